@@ -1,0 +1,151 @@
+/* b200sr — C ABI of the B200-native (sm_100a) diffusion-denoiser kernels.
+ *
+ * This is the drop-in boundary of the hot path: plain pointers, sizes and a CUDA stream; no
+ * torch types.  Every entry point
+ *   - takes DEVICE pointers (bf16 activations are raw uint16 storage, "NHWC" = [N, H, W, C],
+ *     token matrices are row-major [rows, ld]),
+ *   - enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately,
+ *   - never allocates, never synchronises, never throws,
+ *   - returns 0 on success or a negative errno-style code:
+ *       -22 (EINVAL)  bad shape / alignment / flag combination
+ *       -19 (ENODEV)  no sm_100 device or driver entry point unavailable
+ *        -5 (EIO)     CUDA launch error
+ *
+ * The reference (Bluear7878/Remote-Sensing-Vision-Language-Diffusion-Model) has no native code and
+ * no FFI; the interface each function replaces is the torch op sequence at the cited
+ * reference file:line.  The Python binding a maintainer would add is shown in INTEGRATION.md
+ * (ctypes) and implemented in b200sr/_lib.py.
+ */
+#ifndef B200SR_H_
+#define B200SR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library / device introspection. */
+int b200sr_abi_version(void);         /* bumps on any signature change */
+int b200sr_num_sms(void);             /* SM count of the current device, <0 on error */
+
+/* Fused epilogue description shared by the GEMM and implicit-GEMM convolution entry points:
+ *   out = alpha * (acc + bias[n]) + rowvec[group(m), n] + residual[m, n]          (geglu == 0)
+ *   out[m, j] = (acc[m, v(j)] + bias[v(j)]) * gelu_erf(acc[m, g(j)] + bias[g(j)])  (geglu == 1)
+ * where for GEGLU the weight rows were packed by interleaving value / gate rows in groups of 16
+ * (rows 32k..32k+15 = value features 16k..16k+15, rows 32k+16..32k+31 = their gates), the output
+ * has N/2 columns, and alpha / rowvec / residual are not allowed.
+ * group(m) = m / rows_per_group (GEMM) or the image index (convolution).                      */
+typedef struct b200sr_epilogue {
+  const float* bias;        /* [N] fp32 or NULL */
+  const float* rowvec;      /* [groups, N] fp32 or NULL (ResBlock emb add, openaimodel.py:337-348) */
+  int32_t rows_per_group;   /* GEMM only; 0 = single group */
+  const void* residual;     /* bf16 [M, ldr] or NULL */
+  int64_t ldr;
+  void* out;                /* bf16 (or fp32 when out_fp32) [M, ldc] */
+  int64_t ldc;
+  int32_t out_fp32;
+  int32_t geglu;
+  float alpha;
+} b200sr_epilogue;
+
+/* D = A[M,K] * W[N,K]^T with fused epilogue; bf16 operands, fp32 accumulate (tcgen05 / TMEM).
+ * Replaces nn.Linear / 1x1 nn.Conv2d: sgm/modules/attention.py:213-218 (to_q/k/v, to_out),
+ * :84-91 (GEGLU), :106 (FF out), :587/:611 (proj_in/out); openaimodel.py:283-287 (emb_layers),
+ * :311 (skip 1x1), :657-691 (time_embed/label_emb); SR_modules.py:84 (zero_conv).
+ * lda in elements; K % 8 == 0; N % 8 == 0; force_bn = 0 lets the library pick the N tile.    */
+int b200sr_gemm_bf16(const void* A, int64_t lda, const void* W, int32_t M, int32_t N, int32_t K,
+                     const b200sr_epilogue* epi, int32_t force_bn, void* stream);
+
+/* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16, weights [Cout, 3, 3, Cin] bf16, as an
+ * implicit GEMM on the same tcgen05 mainloop (each tap = one shifted TMA box, zero fill = pad).
+ * Replaces nn.Conv2d 3x3: openaimodel.py:121 (Upsample.conv), :190-197 (Downsample.op),
+ * :257 / :294-300 (ResBlock), SR_modules.py:76-80 (ZeroSFT mlp_shared / zero_mul / zero_add),
+ * sr3_modules/unet.py:59-92.  Cin % 64 == 0, Cout % 8 == 0.                                   */
+int b200sr_conv3x3_bf16(const void* x, const void* w, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                        int32_t stride, const b200sr_epilogue* epi, int32_t force_bn, void* stream);
+
+/* Direct 3x3 convolution (pad 1, stride 1) for tiny channel counts: Cin <= 8 (Cout % 8 == 0),
+ * or Cout <= 4 (Cin % 8 == 0).  `addend` (bf16 NHWC, few-in only) is added to the result
+ * (GLVControl `h += guided_hint`, SR_modules.py:521-531).  out_nchw_f32 (few-out only) writes
+ * fp32 NCHW (UNet `out`, openaimodel.py:941-947; wrappers.py:110 `.float()`).                 */
+int b200sr_conv3x3_small(const void* x, const void* w, const float* bias, const void* addend, void* y, int32_t N,
+                         int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t out_nchw_f32, void* stream);
+
+/* GroupNorm over NHWC bf16 with optional fused SiLU and ZeroSFT modulation:
+ *   y = GN(x) * w + b ; [SiLU] ; [y = y * (1 + gamma) + beta ; y = y*s + raw*(1-s)]
+ * util.py:258-276, attention.py:122-125, openaimodel.py:254-258; SR_modules.py:101-110.
+ * workspace: b200sr_group_norm_workspace_bytes() bytes of device scratch.                     */
+size_t b200sr_group_norm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups);
+int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int32_t N, int32_t HW,
+                           int32_t C, int32_t groups, float eps, int32_t silu, const void* sft_gamma,
+                           const void* sft_beta, const void* raw, float control_scale, void* workspace, void* stream);
+
+/* LayerNorm over the last dim of a bf16 [M, C] matrix (attention.py:437-439). */
+int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* bias, int32_t M, int32_t C, float eps,
+                      void* stream);
+
+/* softmax(Q K^T * scale) V for head_dim 64 (attention.py:222-285, SR_modules.py:135-149).
+ * q/k/v are column windows of row-major bf16 matrices: head h of q lives at columns
+ * [q_col + 64h, q_col + 64h + 64) of a [B, Nq, ldq] matrix (so a fused QKV projection is
+ * consumed in place); out is [B, Nq, ldo] with head h at columns [64h, 64h + 64).            */
+int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
+                         const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
+                         int32_t Nq, int32_t Nk, float scale, void* stream);
+
+/* Layout conversion at the nn.Module boundary. */
+int b200sr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, float scale, void* stream);
+int b200sr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, void* stream);
+
+/* Nearest x2 upsample, NHWC bf16 (openaimodel.py:125-145; sr3 unet.py:59-66). */
+int b200sr_upsample2x_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* out[:, :Ca] = a ; out[:, Ca:] = b (+ c).  Rows of bf16 channels (SR_modules.py:88-100,
+ * openaimodel.py:1001, sr3 unet.py:257).  c may be NULL.                                      */
+int b200sr_concat_add(const void* a, int32_t Ca, const void* b, int32_t Cb, const void* c, void* out, int64_t rows,
+                      void* stream);
+
+/* y = a + alpha * b, bf16. */
+int b200sr_axpy_bf16(const void* a, const void* b, void* y, float alpha, int64_t n, void* stream);
+
+/* y = silu(x), bf16 (embedding path: openaimodel.py:281-283, :660-662). */
+int b200sr_silu_bf16(const void* x, void* y, int64_t n, void* stream);
+
+/* Sinusoidal embedding of t[B] (fp32) to bf16 [B, dim]; sin_first = 0: cos|sin (util.py:206-230),
+ * sin_first = 1: sin|cos (sr3 unet.py:19-32).                                                 */
+int b200sr_sinusoid_embedding(const float* t, void* out, int32_t B, int32_t dim, float max_period, int32_t sin_first,
+                              void* stream);
+
+/* Sampler step around the network call (sampling.py:598-621, denoiser.py:67-78, guiders.py:59-74).
+ * scalars (device, fp32[6]) = {sigma, sigma_hat, sigma_next, sigma_quantised, cfg_scale, s_noise}.
+ *   pre : x_hat = x + noise*s_noise*sqrt(sigma_hat^2 - sigma^2) (fp32 NCHW);
+ *         net_in[k] = x_hat / sqrt(sigma_q^2 + 1) for k < cfg_copies (bf16 NHWC [cfg_copies*B,...])
+ *   post: denoised = CFG(eps * -sigma_q + x_hat); x_next = x_hat + (x_hat - denoised)/sigma_hat *
+ *         (sigma_next - sigma_hat); eps is fp32 NCHW [2B,...] (uncond first) when use_cfg.      */
+int b200sr_sampler_pre(const float* x, const float* noise, const float* scalars, float* x_hat, void* net_in, int32_t B,
+                       int32_t C, int32_t HW, int32_t cfg_copies, void* stream);
+int b200sr_sampler_post(const float* eps, const float* x_hat, const float* scalars, float* denoised_out, float* x_next,
+                        int32_t B, int32_t C, int32_t HW, int32_t use_cfg, void* stream);
+int b200sr_euler_from_denoised(const float* denoised, const float* x_hat, const float* scalars, float* x_next,
+                               int64_t n, void* stream);
+
+/* Tile blend (sampling.py:753-756, :830-847): acc[win] += tile * weight, cnt[win] += weight; out = acc / cnt. */
+int b200sr_tile_accumulate(const float* tile, const float* weight, float* acc, float* cnt, int32_t BC, int32_t th,
+                           int32_t tw, int32_t H, int32_t W, int32_t h0, int32_t w0, void* stream);
+int b200sr_tile_normalize(const float* acc, const float* cnt, float* out, int64_t n, void* stream);
+
+/* First-block-cache similarity (DFBCache.py:98-134): result[0] = mean|prev-cur| / (mean|prev| + 1e-6),
+ * result[1] = (result[0] < threshold[0]).  workspace = 2 zeroed doubles (re-zeroed on return). */
+int b200sr_rel_l1_similarity(const void* prev, const void* cur, int64_t n, const float* threshold, void* workspace,
+                             float* result, void* stream);
+
+/* SR3 ancestral update (sr3_modules/diffusion.py:142-176); scalars (device fp32[5]) =
+ * {sqrt_recip_alphas_cumprod[t], sqrt_recipm1_alphas_cumprod[t], coef1[t], coef2[t], log_var[t]}. */
+int b200sr_sr3_update(const float* x, const float* eps, const float* noise, const float* scalars, float* out,
+                      int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SR_H_ */

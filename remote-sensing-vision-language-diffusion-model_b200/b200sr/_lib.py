@@ -1,0 +1,103 @@
+"""ctypes binding of libb200sr.so (the C ABI declared in include/b200sr.h).
+
+The shared library is built in-tree by ``csrc/build.sh`` (or ``__graft_entry__.build()``) and
+lives next to this file.  There is deliberately no fallback: if the library is missing or an
+entry point is absent, importing/using the ops raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sr.so")
+
+ABI_VERSION = 1
+
+c_void_p, c_int, c_i64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class Epilogue(C.Structure):
+    """Mirror of ``b200sr_epilogue`` (include/b200sr.h)."""
+
+    _fields_ = [
+        ("bias", c_void_p),
+        ("rowvec", c_void_p),
+        ("rows_per_group", c_int),
+        ("residual", c_void_p),
+        ("ldr", c_i64),
+        ("out", c_void_p),
+        ("ldc", c_i64),
+        ("out_fp32", c_int),
+        ("geglu", c_int),
+        ("alpha", c_float),
+    ]
+
+
+P = c_void_p
+# name -> (restype, argtypes); must list every symbol include/b200sr.h declares.
+SIGNATURES = {
+    "b200sr_abi_version": (c_int, []),
+    "b200sr_num_sms": (c_int, []),
+    "b200sr_gemm_bf16": (c_int, [P, c_i64, P, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
+    "b200sr_conv3x3_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
+    "b200sr_conv3x3_small": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200sr_group_norm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "b200sr_group_norm_nhwc": (
+        c_int,
+        [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, c_float, P, P],
+    ),
+    "b200sr_layer_norm": (c_int, [P, P, P, P, c_int, c_int, c_float, P]),
+    "b200sr_attention_d64": (
+        c_int,
+        [P, c_i64, c_int, P, c_i64, c_int, P, c_i64, c_int, P, c_i64, c_int, c_int, c_int, c_int, c_float, P],
+    ),
+    "b200sr_nchw_f32_to_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
+    "b200sr_nhwc_bf16_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "b200sr_upsample2x_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "b200sr_concat_add": (c_int, [P, c_int, P, c_int, P, P, c_i64, P]),
+    "b200sr_axpy_bf16": (c_int, [P, P, P, c_float, c_i64, P]),
+    "b200sr_silu_bf16": (c_int, [P, P, c_i64, P]),
+    "b200sr_sinusoid_embedding": (c_int, [P, P, c_int, c_int, c_float, c_int, P]),
+    "b200sr_sampler_pre": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "b200sr_sampler_post": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "b200sr_euler_from_denoised": (c_int, [P, P, P, P, c_i64, P]),
+    "b200sr_tile_accumulate": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200sr_tile_normalize": (c_int, [P, P, P, c_i64, P]),
+    "b200sr_rel_l1_similarity": (c_int, [P, P, c_i64, P, P, P, P]),
+    "b200sr_sr3_update": (c_int, [P, P, P, P, P, c_i64, P]),
+}
+
+_ERRORS = {-22: "EINVAL (bad shape / alignment / flags)", -19: "ENODEV (no sm_100 device / driver)", -5: "EIO (CUDA launch error)"}
+
+_lib = None
+
+
+class B200SRError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libb200sr.so, bind every declared symbol, verify the ABI version."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200SRError(
+            f"{LIB_PATH} not found: build the sm_100a extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or csrc/build.sh). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200sr_abi_version() != ABI_VERSION:
+        raise B200SRError(f"libb200sr.so ABI {lib.b200sr_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise B200SRError(f"{what} failed: {_ERRORS.get(rc, rc)}")

@@ -1,0 +1,409 @@
+"""Operator layer: torch tensors in, libb200sr.so kernels underneath (through the C ABI).
+
+Conventions
+-----------
+* activations are contiguous **bf16, channels last**: images ``[N, H, W, C]``, tokens ``[B, T, C]``;
+* parameters handed to the kernels are *packed* once by the modules (``pack_linear`` /
+  ``pack_conv3x3``): bf16, K-major, conv taps flattened as ``K = (kh*3 + kw) * Cin + c``;
+* biases / norm affine parameters stay fp32;
+* every call is enqueued on ``torch.cuda.current_stream()``; nothing synchronises.
+
+There is no CPU path and no torch fallback here: tensors that are not CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.B200SRError(f"{name}: expected a CUDA tensor (b200sr has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.B200SRError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.B200SRError(f"{name}: expected a contiguous tensor")
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        if torch.cuda.is_current_stream_capturing() and ws is not None:
+            raise _lib.B200SRError("workspace growth during CUDA-graph capture; run one eager warm-up step first")
+        ws = torch.zeros(max(nbytes // 4 + 1, 1 << 18), dtype=torch.float32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter packing (runs once per module, on whatever device the parameter lives on)
+# ------------------------------------------------------------------------------------------------
+def pack_linear(weight: torch.Tensor) -> torch.Tensor:
+    """nn.Linear / 1x1-conv weight [N, K(,1,1)] fp32 -> bf16 [N, K] (K-major B operand)."""
+    w = weight.detach().reshape(weight.shape[0], -1)
+    return w.to(bf16).contiguous()
+
+
+def pack_conv3x3(weight: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d weight [Cout, Cin, 3, 3] fp32 -> bf16 [Cout, 9*Cin] with K = (kh*3+kw)*Cin + c."""
+    co, ci, kh, kw = weight.shape
+    assert kh == 3 and kw == 3
+    return weight.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci).to(bf16).contiguous()
+
+
+def geglu_interleave_index(inner: int, device=None) -> torch.Tensor:
+    """Row permutation for the GEGLU projection (attention.py:84-91): the reference computes
+    ``x, gate = proj(x).chunk(2)``; the kernel epilogue wants value / gate rows of the same 16
+    output features adjacent: packed rows 32k..32k+15 = value 16k..16k+15, 32k+16..32k+31 = gate."""
+    assert inner % 16 == 0
+    j = torch.arange(inner, device=device)
+    val_pos = (j // 16) * 32 + (j % 16)
+    idx = torch.empty(2 * inner, dtype=torch.long, device=device)
+    idx[val_pos] = j
+    idx[val_pos + 16] = j + inner
+    return idx
+
+
+def pack_geglu(weight: torch.Tensor, bias: torch.Tensor):
+    inner = weight.shape[0] // 2
+    idx = geglu_interleave_index(inner, weight.device)
+    return weight.detach()[idx].to(bf16).contiguous(), bias.detach()[idx].float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# dense contractions
+# ------------------------------------------------------------------------------------------------
+def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha) -> Epilogue:
+    e = Epilogue()
+    e.bias = _ptr(bias)
+    e.rowvec = _ptr(rowvec)
+    e.rows_per_group = rows_per_group
+    e.residual = _ptr(residual)
+    e.ldr = ldr
+    e.out = out.data_ptr()
+    e.ldc = ldc
+    e.out_fp32 = int(out_fp32)
+    e.geglu = int(geglu)
+    e.alpha = float(alpha)
+    return e
+
+
+def gemm(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    bias: Optional[torch.Tensor] = None,
+    *,
+    residual: Optional[torch.Tensor] = None,
+    rowvec: Optional[torch.Tensor] = None,
+    rows_per_group: int = 0,
+    geglu: bool = False,
+    alpha: float = 1.0,
+    out: Optional[torch.Tensor] = None,
+    out_fp32: bool = False,
+    force_bn: int = 0,
+) -> torch.Tensor:
+    """``out = alpha * (a @ w.T + bias) + rowvec[group] + residual`` (or GEGLU).  a: [..., K] bf16
+    (last-dim contiguous, uniform row stride), w: [N, K] packed bf16.  `out` may be a column
+    slice of a wider row-major tensor (its row stride is honoured)."""
+    _req(w, bf16, "gemm.w")
+    if a.dtype != bf16 or not a.is_cuda:
+        raise _lib.B200SRError("gemm.a: expected CUDA bf16")
+    K = a.shape[-1]
+    N = w.shape[0]
+    a2 = a.reshape(-1, K)
+    if a2.stride(-1) != 1:
+        a2 = a2.contiguous()
+    M, lda = a2.shape[0], a2.stride(0)
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty(*a.shape[:-1], n_out, dtype=torch.float32 if out_fp32 else bf16, device=a.device)
+    o2 = out.reshape(-1, n_out) if out.is_contiguous() else out
+    assert o2.shape[-1] == n_out and o2.stride(-1) == 1
+    ldc = o2.stride(-2) if o2.dim() >= 2 else n_out
+    ldr = 0
+    if residual is not None:
+        r2 = residual if residual.dim() == 2 else residual.reshape(-1, residual.shape[-1])
+        assert r2.dtype == bf16 and r2.stride(-1) == 1
+        ldr = r2.stride(0)
+    e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha)
+    rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
+    check(rc, f"gemm M={M} N={N} K={K}")
+    return out
+
+
+def conv3x3(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    bias: Optional[torch.Tensor] = None,
+    *,
+    stride: int = 1,
+    rowvec: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    alpha: float = 1.0,
+    out: Optional[torch.Tensor] = None,
+    force_bn: int = 0,
+) -> torch.Tensor:
+    """3x3 conv, pad 1.  x: [N, H, W, Cin] bf16; w: packed [Cout, 9*Cin]; rowvec: fp32 [N, Cout]
+    (added per image: ResBlock emb); residual: bf16 [N, OH, OW, Cout]."""
+    _req(x, bf16, "conv3x3.x")
+    _req(w, bf16, "conv3x3.w")
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    assert w.shape[1] == 9 * cin
+    oh, ow = h // stride, wd // stride
+    if out is None:
+        out = torch.empty(n, oh, ow, cout, dtype=bf16, device=x.device)
+    ldc = out.stride(2)
+    ldr = residual.stride(2) if residual is not None else 0
+    e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha)
+    rc = _lib.load().b200sr_conv3x3_bf16(
+        x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, C.byref(e), force_bn, _stream()
+    )
+    check(rc, f"conv3x3 N={n} H={h} W={wd} Cin={cin} Cout={cout} s={stride}")
+    return out
+
+
+def conv3x3_small(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    *,
+    addend: Optional[torch.Tensor] = None,
+    out_nchw_f32: bool = False,
+) -> torch.Tensor:
+    _req(x, bf16, "conv3x3_small.x")
+    _req(w, bf16, "conv3x3_small.w")
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    if out_nchw_f32:
+        out = torch.empty(n, cout, h, wd, dtype=torch.float32, device=x.device)
+    else:
+        out = torch.empty(n, h, wd, cout, dtype=bf16, device=x.device)
+    rc = _lib.load().b200sr_conv3x3_small(
+        x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(addend), out.data_ptr(), n, h, wd, cin, cout, int(out_nchw_f32),
+        _stream()
+    )
+    check(rc, f"conv3x3_small Cin={cin} Cout={cout}")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+def group_norm(
+    x: torch.Tensor,
+    weight: Optional[torch.Tensor],
+    bias: Optional[torch.Tensor],
+    *,
+    groups: int = 32,
+    eps: float = 1e-5,
+    silu: bool = False,
+    sft_gamma: Optional[torch.Tensor] = None,
+    sft_beta: Optional[torch.Tensor] = None,
+    raw: Optional[torch.Tensor] = None,
+    control_scale: float = 1.0,
+) -> torch.Tensor:
+    """GroupNorm over channels-last x: [N, ..., C] bf16 (+SiLU) (+ZeroSFT modulation)."""
+    _req(x, bf16, "group_norm.x")
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    lib = _lib.load()
+    ws = _workspace(x.device, lib.b200sr_group_norm_workspace_bytes(n, hw, c, groups))
+    y = torch.empty_like(x)
+    rc = lib.b200sr_group_norm_nhwc(
+        x.data_ptr(), y.data_ptr(), _ptr(weight), _ptr(bias), n, hw, c, groups, eps, int(silu), _ptr(sft_gamma),
+        _ptr(sft_beta), _ptr(raw), float(control_scale), ws.data_ptr(), _stream()
+    )
+    check(rc, f"group_norm N={n} HW={hw} C={c}")
+    return y
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _req(x, bf16, "layer_norm.x")
+    c = x.shape[-1]
+    m = x.numel() // c
+    y = torch.empty_like(x)
+    rc = _lib.load().b200sr_layer_norm(x.data_ptr(), y.data_ptr(), weight.data_ptr(), bias.data_ptr(), m, c, eps, _stream())
+    check(rc, f"layer_norm M={m} C={c}")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attention(
+    q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, q_col: int = 0, k_col: int = 0, v_col: int = 0,
+    scale: Optional[float] = None
+) -> torch.Tensor:
+    """q: [B, Nq, ldq], k / v: [B, Nk, ld] row-major bf16 matrices; head h of q occupies columns
+    [q_col + 64h, q_col + 64h + 64) (likewise k_col / v_col) so a fused QKV buffer can be passed
+    three times with different offsets.  Returns [B, Nq, heads*64]."""
+    for t, nme in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, bf16, f"attention.{nme}")
+    b, nq, ldq = q.shape
+    nk = k.shape[1]
+    out = torch.empty(b, nq, heads * 64, dtype=bf16, device=q.device)
+    rc = _lib.load().b200sr_attention_d64(
+        q.data_ptr(), ldq, q_col, k.data_ptr(), k.shape[2], k_col, v.data_ptr(), v.shape[2], v_col, out.data_ptr(),
+        heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _stream()
+    )
+    check(rc, f"attention B={b} H={heads} Nq={nq} Nk={nk}")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# layout / elementwise
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc_bf16(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """[N, C, H, W] fp32 -> [N, H, W, C] bf16 (times `scale`)."""
+    _req(x, torch.float32, "nchw_to_nhwc.x")
+    n, c, h, w = x.shape
+    y = torch.empty(n, h, w, c, dtype=bf16, device=x.device)
+    check(_lib.load().b200sr_nchw_f32_to_nhwc_bf16(x.data_ptr(), y.data_ptr(), n, c, h * w, float(scale), _stream()),
+          "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    _req(x, bf16, "nhwc_to_nchw.x")
+    n, h, w, c = x.shape
+    y = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
+    check(_lib.load().b200sr_nhwc_bf16_to_nchw_f32(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()), "nhwc_to_nchw")
+    return y
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _req(x, bf16, "upsample2x.x")
+    n, h, w, c = x.shape
+    y = torch.empty(n, 2 * h, 2 * w, c, dtype=bf16, device=x.device)
+    check(_lib.load().b200sr_upsample2x_nhwc(x.data_ptr(), y.data_ptr(), n, h, w, c, _stream()), "upsample2x")
+    return y
+
+
+def concat_add(a: Optional[torch.Tensor], b: torch.Tensor, c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cat([a, b (+ c)], channel dim) for channels-last bf16 tensors."""
+    _req(b, bf16, "concat_add.b")
+    ca = 0 if a is None else a.shape[-1]
+    cb = b.shape[-1]
+    rows = b.numel() // cb
+    out = torch.empty(*b.shape[:-1], ca + cb, dtype=bf16, device=b.device)
+    check(_lib.load().b200sr_concat_add(_ptr(a), ca, b.data_ptr(), cb, _ptr(c), out.data_ptr(), rows, _stream()),
+          "concat_add")
+    return out
+
+
+def axpy(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    _req(a, bf16, "axpy.a")
+    _req(b, bf16, "axpy.b")
+    y = torch.empty_like(a)
+    check(_lib.load().b200sr_axpy_bf16(a.data_ptr(), b.data_ptr(), y.data_ptr(), float(alpha), a.numel(), _stream()),
+          "axpy")
+    return y
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    _req(x, bf16, "silu.x")
+    y = torch.empty_like(x)
+    check(_lib.load().b200sr_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu")
+    return y
+
+
+def sinusoid_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0, sin_first: bool = False) -> torch.Tensor:
+    t = t.reshape(-1).to(torch.float32).contiguous()
+    if not t.is_cuda:
+        raise _lib.B200SRError("sinusoid_embedding: expected a CUDA tensor")
+    out = torch.empty(t.numel(), dim, dtype=bf16, device=t.device)
+    check(_lib.load().b200sr_sinusoid_embedding(t.data_ptr(), out.data_ptr(), t.numel(), dim, float(max_period),
+                                                int(sin_first), _stream()), "sinusoid_embedding")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler-side kernels
+# ------------------------------------------------------------------------------------------------
+def sampler_pre(x: torch.Tensor, noise: Optional[torch.Tensor], scalars: torch.Tensor, cfg_copies: int = 2):
+    """Returns (x_hat fp32 NCHW, net_in bf16 NHWC [cfg_copies*B, H, W, C])."""
+    _req(x, torch.float32, "sampler_pre.x")
+    b, c, h, w = x.shape
+    x_hat = torch.empty_like(x)
+    net_in = torch.empty(cfg_copies * b, h, w, c, dtype=bf16, device=x.device)
+    check(_lib.load().b200sr_sampler_pre(x.data_ptr(), _ptr(noise), scalars.data_ptr(), x_hat.data_ptr(),
+                                         net_in.data_ptr(), b, c, h * w, cfg_copies, _stream()), "sampler_pre")
+    return x_hat, net_in
+
+
+def sampler_post(eps: torch.Tensor, x_hat: torch.Tensor, scalars: torch.Tensor, use_cfg: bool = True,
+                 want_denoised: bool = True):
+    """eps: fp32 NCHW [2B or B, C, H, W].  Returns (x_next, denoised)."""
+    _req(eps, torch.float32, "sampler_post.eps")
+    b, c, h, w = x_hat.shape
+    x_next = torch.empty_like(x_hat)
+    den = torch.empty_like(x_hat) if want_denoised else None
+    check(_lib.load().b200sr_sampler_post(eps.data_ptr(), x_hat.data_ptr(), scalars.data_ptr(), _ptr(den),
+                                          x_next.data_ptr(), b, c, h * w, int(use_cfg), _stream()), "sampler_post")
+    return x_next, den
+
+
+def euler_from_denoised(denoised: torch.Tensor, x_hat: torch.Tensor, scalars: torch.Tensor) -> torch.Tensor:
+    x_next = torch.empty_like(x_hat)
+    check(_lib.load().b200sr_euler_from_denoised(denoised.data_ptr(), x_hat.data_ptr(), scalars.data_ptr(),
+                                                 x_next.data_ptr(), x_hat.numel(), _stream()), "euler_from_denoised")
+    return x_next
+
+
+def tile_accumulate(tile: torch.Tensor, weight: torch.Tensor, acc: torch.Tensor, cnt: torch.Tensor, h0: int, w0: int):
+    b, c, th, tw = tile.shape
+    H, W = acc.shape[-2:]
+    check(_lib.load().b200sr_tile_accumulate(tile.data_ptr(), weight.data_ptr(), acc.data_ptr(), cnt.data_ptr(), b * c,
+                                             th, tw, H, W, h0, w0, _stream()), "tile_accumulate")
+
+
+def tile_normalize(acc: torch.Tensor, cnt: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(acc)
+    check(_lib.load().b200sr_tile_normalize(acc.data_ptr(), cnt.data_ptr(), out.data_ptr(), acc.numel(), _stream()),
+          "tile_normalize")
+    return out
+
+
+_rel_ws: dict = {}
+
+
+def rel_l1_similarity(prev: torch.Tensor, cur: torch.Tensor, threshold: torch.Tensor) -> torch.Tensor:
+    """Returns a device fp32[2]: (diff, diff < threshold) — DFBCache.are_two_tensors_similar."""
+    _req(prev, bf16, "rel_l1.prev")
+    _req(cur, bf16, "rel_l1.cur")
+    key = (prev.device.type, prev.device.index)
+    ws = _rel_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(2, dtype=torch.float64, device=prev.device)
+        _rel_ws[key] = ws
+    res = torch.empty(2, dtype=torch.float32, device=prev.device)
+    check(_lib.load().b200sr_rel_l1_similarity(prev.data_ptr(), cur.data_ptr(), prev.numel(), threshold.data_ptr(),
+                                               ws.data_ptr(), res.data_ptr(), _stream()), "rel_l1_similarity")
+    return res
+
+
+def sr3_update(x: torch.Tensor, eps: torch.Tensor, noise: Optional[torch.Tensor], scalars: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(x)
+    check(_lib.load().b200sr_sr3_update(x.data_ptr(), eps.data_ptr(), _ptr(noise), scalars.data_ptr(), out.data_ptr(),
+                                        x.numel(), _stream()), "sr3_update")
+    return out

@@ -1,0 +1,314 @@
+// b200sr — flash-style attention (online softmax) on tcgen05/TMEM for head_dim 64, non-causal.
+//
+// Reference semantics: softmax(Q K^T / sqrt(64)) V per head, heads = C / 64, no mask, no dropout
+//   sgm/modules/attention.py:222-285 (CrossAttention -> F.scaled_dot_product_attention)
+//   models/modules/SR_modules.py:135-149 (ZeroCrossAttn uses the same CrossAttention)
+//
+// One CTA = 128 query rows of one (batch, head).  Per 128-key block:
+//   S[128x128] = Q K^T          tcgen05.mma SS  (Q, K tiles in smem, K-major, 128B swizzle)
+//   P = exp2(S*c - m)           4 softmax warps, one thread per query row, S read from TMEM,
+//                               P written back to TMEM as packed bf16 (never touches smem)
+//   O[128x64] += P V            tcgen05.mma TS  (A = P in TMEM, B = V tile in smem, MN-major)
+// O stays in TMEM for the whole KV loop; it is rescaled only when the running row maximum has
+// grown by more than 2^8 since the last rescale (the softmax sum uses the same stale maximum, so
+// the final O / l is exact).  Two CTAs are resident per SM (80 KiB smem, 256 TMEM columns each)
+// so one CTA's exponentials overlap the other's MMAs.
+//
+// Q, K and V are addressed as column windows of row-major bf16 matrices ([B, N, ld] with a
+// column offset), so the fused QKV GEMM output is consumed in place.
+#include "common.cuh"
+
+namespace b200sr {
+
+static constexpr int ATT_BM = 128;   // query rows per CTA
+static constexpr int ATT_BN = 128;   // keys per block
+static constexpr int ATT_D = 64;     // head dim
+static constexpr int ATT_THREADS = 192;
+static constexpr int ATT_STAGES = 2;
+static constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KiB
+static constexpr int ATT_TMEM_COLS = 256;
+static constexpr int ATT_COL_S = 0;     // 128 fp32 columns
+static constexpr int ATT_COL_P = 128;   // 64 columns of packed bf16 pairs
+static constexpr int ATT_COL_O = 192;   // 64 fp32 columns
+
+struct AttnParams {
+  int B, H, Nq, Nk;
+  int q_col, k_col, v_col;  // column offsets (elements) of head 0 inside each matrix row
+  __nv_bfloat16* out;
+  long long ldo;  // elements per output row ([B*Nq, ldo], head h at columns h*64)
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + ATT_TILE_BYTES;  // stage s: K at s*32K, V at s*32K + 16K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ATT_STAGES * 2 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                 // [ATT_STAGES]
+  uint64_t* kv_empty = kv_full + ATT_STAGES;    // [ATT_STAGES]
+  uint64_t* s_full = kv_empty + ATT_STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.Nk + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);  // one arrive per softmax warp
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col + h * ATT_D, q0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + stage * 2 * ATT_TILE_BYTES;
+        uint8_t* sV = sK + ATT_TILE_BYTES;
+        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_3d(sK, &tmK, &kv_full[stage], p.k_col + h * ATT_D, j * ATT_BN, b);
+        tma_load_3d(sV, &tmV, &kv_full[stage], p.v_col + h * ATT_D, j * ATT_BN, b);
+        if (++stage == ATT_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16_f32(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K^T (K-major)
+      const uint32_t idesc_o = umma_idesc_bf16_f32(ATT_BM, ATT_D, 0, 1);   // P (tmem)  x V (MN-major)
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      // S(0)
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sKV), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem + ATT_COL_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
+      }
+      for (int j = 0; j < nblk; ++j) {
+        // O += P(j) V(j)
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        {
+          const uint32_t sV = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+          // V tile: row = key (128 B of d), 8-key groups 1024 B apart; MN-major B operand.
+          const uint64_t vdesc = umma_smem_desc_sw128(sV, 1024, 1024);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows = 2048 B
+            umma_ts(tmem + ATT_COL_O, tmem + ATT_COL_P + 8 * k, vdesc + (2048 >> 4) * k, idesc_o, (j | k) != 0);
+          }
+          umma_commit(&kv_empty[stage]);
+          if (j + 1 == nblk) umma_commit(o_done);
+        }
+        if (++stage == ATT_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (j + 1 < nblk) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after();
+          const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sKV + stage * 2 * ATT_TILE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k)
+            umma_ss(tmem + ATT_COL_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ================================ softmax / correction / epilogue ================================
+    const int sub = warp & 3;
+    const int r = sub * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
+    float m_used = -INFINITY;  // maximum the exponentials are currently taken against (log2 units)
+    float l = 0.f;             // running sum of exponentials
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t a[32];
+        tmem_ld32(tmem + lane_base + ATT_COL_S + c * 32, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(a[i]);
+      }
+      tmem_ld_wait();
+      const int kv_left = p.Nk - j * ATT_BN;
+      if (kv_left < ATT_BN) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) s[i] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+      mx *= p.scale_log2;
+      // lazy rescale: only when the maximum grew by more than 8 (factor 256) since the last one
+      const bool grow = mx > m_used + 8.0f;
+      if (j == 0) {
+        m_used = mx;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        float alpha = 1.0f;
+        if (grow) {
+          alpha = exp2f(m_used - mx);
+          m_used = mx;
+          l *= alpha;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem + lane_base + ATT_COL_O + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem + lane_base + ATT_COL_O + c * 32, o);
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e0 = exp2f(fmaf(s[c * 64 + 2 * i], p.scale_log2, -m_used));
+          const float e1 = exp2f(fmaf(s[c * 64 + 2 * i + 1], p.scale_log2, -m_used));
+          sum += e0 + e1;
+          pk[i] = pack_bf16x2(e0, e1);
+        }
+        tmem_st32(tmem + lane_base + ATT_COL_P + c * 32, pk);
+      }
+      l += sum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int q = q0 + r;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem + lane_base + ATT_COL_O + c * 32, o);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * ATT_D + c * 32;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+          reinterpret_cast<uint4*>(dst)[v] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, ATT_TMEM_COLS);
+}
+
+static int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, int batch, int width_cols) {
+  uint64_t dims[3] = {static_cast<uint64_t>(width_cols), static_cast<uint64_t>(rows), static_cast<uint64_t>(batch)};
+  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(rows) * ld * 2};
+  uint32_t box[3] = {ATT_D, 128, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+
+// q: [B, Nq, ldq] window at q_col; k, v: [B, Nk, ldk / ldv] windows; out: [B, Nq, ldo], head h at h*64.
+int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
+                  long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
+                  cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return B200SR_EINVAL;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (q_col % 8) || (k_col % 8) || (v_col % 8))
+    return B200SR_EINVAL;
+  if (q_col + H * ATT_D > ldq || k_col + H * ATT_D > ldk || v_col + H * ATT_D > ldv || H * ATT_D > ldo)
+    return B200SR_EINVAL;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_map3(&tmQ, q, ldq, Nq, B, static_cast<int>(ldq));
+  if (rc) return rc;
+  rc = make_map3(&tmK, k, ldk, Nk, B, static_cast<int>(ldk));
+  if (rc) return rc;
+  rc = make_map3(&tmV, v, ldv, Nk, B, static_cast<int>(ldv));
+  if (rc) return rc;
+  AttnParams p;
+  p.B = B;
+  p.H = H;
+  p.Nq = Nq;
+  p.Nk = Nk;
+  p.q_col = q_col;
+  p.k_col = k_col;
+  p.v_col = v_col;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const size_t smem_bytes = ATT_TILE_BYTES * (1 + 2 * ATT_STAGES) + 1024 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_bytes)) != cudaSuccess)
+      return B200SR_ELAUNCH;
+    attr_set = true;
+  }
+  dim3 grid((Nq + ATT_BM - 1) / ATT_BM, H, B);
+  attention_d64_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+}  // namespace b200sr

@@ -1,0 +1,231 @@
+// b200sr — extern "C" entry points (include/b200sr.h) and shared host utilities.
+#include "../../include/b200sr.h"
+#include "common.cuh"
+
+namespace b200sr {
+
+// ---- host utilities -----------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return B200SR_ENODEV;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return B200SR_EINVAL;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return B200SR_EINVAL;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (gstr[i] % 16 != 0) return B200SR_EINVAL;
+  }
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                         gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200SR_OK : B200SR_EINVAL;
+}
+
+// ---- forward declarations of the kernel launchers -------------------------------------------
+int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, const EpilogueArgs& e, int force_bn,
+              cudaStream_t stream);
+int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride,
+                 const EpilogueArgs& e, int force_bn, cudaStream_t stream);
+size_t group_norm_workspace_bytes(int N, int HW, int C, int groups);
+int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int N, int HW, int C, int groups,
+                    float eps, int silu, const void* sft_gamma, const void* sft_beta, const void* raw,
+                    float control_scale, float* workspace, cudaStream_t stream);
+int layer_norm(const void* x, void* y, const float* weight, const float* bias, int M, int C, float eps,
+               cudaStream_t stream);
+int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
+                  long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
+                  cudaStream_t stream);
+int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int HW, float scale, cudaStream_t stream);
+int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStream_t stream);
+int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream);
+int concat_add(const void* a, int Ca, const void* b, int Cb, const void* c, void* out, long long rows,
+               cudaStream_t stream);
+int axpy_bf16(const void* a, const void* b, void* y, float alpha, long long n, cudaStream_t stream);
+int silu_bf16(const void* x, void* y, long long n, cudaStream_t stream);
+int sinusoid_embedding(const float* t, void* out, int B, int dim, float max_period, int sin_first,
+                       cudaStream_t stream);
+int conv3x3_small(const void* x, const void* w, const float* bias, const void* addend, void* y, int N, int H, int W,
+                  int Cin, int Cout, int out_nchw_f32, cudaStream_t stream);
+int sampler_pre(const float* x, const float* noise, const float* scalars, float* x_hat, void* net_in, int B, int C,
+                int HW, int cfg_copies, cudaStream_t stream);
+int sampler_post(const float* eps, const float* x_hat, const float* scalars, float* denoised_out, float* x_next, int B,
+                 int C, int HW, int use_cfg, cudaStream_t stream);
+int euler_from_denoised(const float* denoised, const float* x_hat, const float* scalars, float* x_next, long long n,
+                        cudaStream_t stream);
+int tile_accumulate(const float* tile, const float* weight, float* acc, float* cnt, int BC, int th, int tw, int H, int W,
+                    int h0, int w0, cudaStream_t stream);
+int tile_normalize(const float* acc, const float* cnt, float* out, long long n, cudaStream_t stream);
+int rel_l1_similarity(const void* prev, const void* cur, long long n, const float* threshold, double* workspace,
+                      float* result, cudaStream_t stream);
+int sr3_update(const float* x, const float* eps, const float* noise, const float* scalars, float* out, long long n,
+               cudaStream_t stream);
+
+static EpilogueArgs to_args(const b200sr_epilogue* e) {
+  EpilogueArgs a;
+  a.bias = e->bias;
+  a.rowvec = e->rowvec;
+  a.rows_per_group = e->rows_per_group;
+  a.residual = e->residual;
+  a.ldr = e->ldr;
+  a.out = e->out;
+  a.ldc = e->ldc;
+  a.out_fp32 = e->out_fp32;
+  a.geglu = e->geglu;
+  a.alpha = e->alpha;
+  return a;
+}
+
+}  // namespace b200sr
+
+using namespace b200sr;
+#define S(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int b200sr_abi_version(void) { return 1; }
+int b200sr_num_sms(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200SR_ENODEV;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200SR_ENODEV;
+  return n;
+}
+
+int b200sr_gemm_bf16(const void* A, int64_t lda, const void* W, int32_t M, int32_t N, int32_t K,
+                     const b200sr_epilogue* epi, int32_t force_bn, void* stream) {
+  if (A == nullptr || W == nullptr || epi == nullptr) return B200SR_EINVAL;
+  return gemm_bf16(A, lda, W, M, N, K, to_args(epi), force_bn, S(stream));
+}
+int b200sr_conv3x3_bf16(const void* x, const void* w, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                        int32_t stride, const b200sr_epilogue* epi, int32_t force_bn, void* stream) {
+  if (x == nullptr || w == nullptr || epi == nullptr) return B200SR_EINVAL;
+  return conv3x3_bf16(x, w, N, H, W, Cin, Cout, stride, to_args(epi), force_bn, S(stream));
+}
+int b200sr_conv3x3_small(const void* x, const void* w, const float* bias, const void* addend, void* y, int32_t N,
+                         int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t out_nchw_f32, void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr) return B200SR_EINVAL;
+  return conv3x3_small(x, w, bias, addend, y, N, H, W, Cin, Cout, out_nchw_f32, S(stream));
+}
+size_t b200sr_group_norm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups) {
+  if (N <= 0 || HW <= 0 || C < 8 || groups <= 0) return 0;
+  return group_norm_workspace_bytes(N, HW, C, groups);
+}
+int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int32_t N, int32_t HW,
+                           int32_t C, int32_t groups, float eps, int32_t silu, const void* sft_gamma,
+                           const void* sft_beta, const void* raw, float control_scale, void* workspace, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return group_norm_nhwc(x, y, weight, bias, N, HW, C, groups, eps, silu, sft_gamma, sft_beta, raw, control_scale,
+                         reinterpret_cast<float*>(workspace), S(stream));
+}
+int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* bias, int32_t M, int32_t C, float eps,
+                      void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return layer_norm(x, y, weight, bias, M, C, eps, S(stream));
+}
+int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
+                         const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
+                         int32_t Nq, int32_t Nk, float scale, void* stream) {
+  if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return B200SR_EINVAL;
+  return attention_d64(q, ldq, q_col, k, ldk, k_col, v, ldv, v_col, out, ldo, B, H, Nq, Nk, scale, S(stream));
+}
+int b200sr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, float scale, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return nchw_f32_to_nhwc_bf16(x, y, N, C, HW, scale, S(stream));
+}
+int b200sr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return nhwc_bf16_to_nchw_f32(x, y, N, C, HW, S(stream));
+}
+int b200sr_upsample2x_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return upsample2x_nhwc(x, y, N, H, W, C, S(stream));
+}
+int b200sr_concat_add(const void* a, int32_t Ca, const void* b, int32_t Cb, const void* c, void* out, int64_t rows,
+                      void* stream) {
+  if ((a == nullptr && Ca > 0) || b == nullptr || out == nullptr) return B200SR_EINVAL;
+  return concat_add(a, Ca, b, Cb, c, out, rows, S(stream));
+}
+int b200sr_axpy_bf16(const void* a, const void* b, void* y, float alpha, int64_t n, void* stream) {
+  if (a == nullptr || b == nullptr || y == nullptr) return B200SR_EINVAL;
+  return axpy_bf16(a, b, y, alpha, n, S(stream));
+}
+int b200sr_silu_bf16(const void* x, void* y, int64_t n, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return silu_bf16(x, y, n, S(stream));
+}
+int b200sr_sinusoid_embedding(const float* t, void* out, int32_t B, int32_t dim, float max_period, int32_t sin_first,
+                              void* stream) {
+  if (t == nullptr || out == nullptr) return B200SR_EINVAL;
+  return sinusoid_embedding(t, out, B, dim, max_period, sin_first, S(stream));
+}
+int b200sr_sampler_pre(const float* x, const float* noise, const float* scalars, float* x_hat, void* net_in, int32_t B,
+                       int32_t C, int32_t HW, int32_t cfg_copies, void* stream) {
+  if (x == nullptr || scalars == nullptr || x_hat == nullptr || net_in == nullptr) return B200SR_EINVAL;
+  return sampler_pre(x, noise, scalars, x_hat, net_in, B, C, HW, cfg_copies, S(stream));
+}
+int b200sr_sampler_post(const float* eps, const float* x_hat, const float* scalars, float* denoised_out, float* x_next,
+                        int32_t B, int32_t C, int32_t HW, int32_t use_cfg, void* stream) {
+  if (eps == nullptr || x_hat == nullptr || scalars == nullptr || x_next == nullptr) return B200SR_EINVAL;
+  return sampler_post(eps, x_hat, scalars, denoised_out, x_next, B, C, HW, use_cfg, S(stream));
+}
+int b200sr_euler_from_denoised(const float* denoised, const float* x_hat, const float* scalars, float* x_next,
+                               int64_t n, void* stream) {
+  if (denoised == nullptr || x_hat == nullptr || scalars == nullptr || x_next == nullptr) return B200SR_EINVAL;
+  return euler_from_denoised(denoised, x_hat, scalars, x_next, n, S(stream));
+}
+int b200sr_tile_accumulate(const float* tile, const float* weight, float* acc, float* cnt, int32_t BC, int32_t th,
+                           int32_t tw, int32_t H, int32_t W, int32_t h0, int32_t w0, void* stream) {
+  if (tile == nullptr || weight == nullptr || acc == nullptr || cnt == nullptr) return B200SR_EINVAL;
+  return tile_accumulate(tile, weight, acc, cnt, BC, th, tw, H, W, h0, w0, S(stream));
+}
+int b200sr_tile_normalize(const float* acc, const float* cnt, float* out, int64_t n, void* stream) {
+  if (acc == nullptr || cnt == nullptr || out == nullptr) return B200SR_EINVAL;
+  return tile_normalize(acc, cnt, out, n, S(stream));
+}
+int b200sr_rel_l1_similarity(const void* prev, const void* cur, int64_t n, const float* threshold, void* workspace,
+                             float* result, void* stream) {
+  if (prev == nullptr || cur == nullptr || threshold == nullptr || workspace == nullptr || result == nullptr)
+    return B200SR_EINVAL;
+  return rel_l1_similarity(prev, cur, n, threshold, reinterpret_cast<double*>(workspace), result, S(stream));
+}
+int b200sr_sr3_update(const float* x, const float* eps, const float* noise, const float* scalars, float* out,
+                      int64_t n, void* stream) {
+  if (x == nullptr || eps == nullptr || scalars == nullptr || out == nullptr) return B200SR_EINVAL;
+  return sr3_update(x, eps, noise, scalars, out, n, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,493 @@
+// b200sr — tcgen05/TMEM GEMM and implicit-GEMM 3x3 convolution for sm_100a.
+//
+// One persistent, warp-specialised kernel serves every dense contraction on the denoiser path
+// (reference call sites: nn.Linear in sgm/modules/attention.py:213-218,:87,:106,:587,:611 and
+// openaimodel.py:283-287,:660-662; nn.Conv2d 3x3/1x1 in openaimodel.py:121,:190-197,:257,:294-300,:311
+// and models/modules/SR_modules.py:76-84):
+//
+//   D[M, N] = A[M, K] * W[N, K]^T            bf16 operands, fp32 accumulation in TMEM
+//
+//   mode 0  GEMM      A is a row-major [M, K] matrix (tokens x channels / NHWC pixels x channels)
+//   mode 1  conv3x3   A is an NHWC image; the K loop runs over 9 taps x Cin/64 chunks and each
+//                     chunk is one 4-D TMA box shifted by the tap offset (zero fill = padding 1)
+//   mode 2  conv3x3 stride 2 (Downsample): the image is viewed as [N, H/2, 2, W/2, 2*C] so each
+//                     tap is again one rectangular 5-D TMA box
+//
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM owner,
+// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Two accumulator
+// stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1.
+//
+// Fused epilogues: +bias[N], +rowvec[group, N] (ResBlock timestep-embedding add, one group per
+// image), alpha scale, +residual[M, N], GEGLU (value/gate interleaved in 16-column groups by the
+// weight packer), bf16 or fp32 output.
+#include "common.cuh"
+
+namespace b200sr {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+static constexpr int UMMA_K = 16;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+static constexpr int MAX_STAGES = 8;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int TMEM_COLS = 512;
+static constexpr int ACC_STAGE_COLS = 256;
+
+struct GemmParams {
+  int mode;
+  int M, N, K;
+  int BN;
+  int num_m_blocks, num_n_blocks;
+  int k_iters;
+  int kc_per_tap;
+  int Cin;
+  int OH, OW, NB;
+  int bw_log2, bh_log2, bn_log2;
+  int tiles_w, tiles_h, tiles_n;
+  int stages;
+  // epilogue
+  const float* bias;
+  const float* rowvec;
+  int rows_per_group;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  void* out;
+  long long ldc;
+  int out_fp32;
+  int geglu;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // Round the dynamic smem base up to 1024 B (swizzle-128B atoms are 1024 B aligned).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stage_bytes = A_STAGE_BYTES + p.BN * (BLOCK_K * 2);
+  const int stages = p.stages;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks;
+        const int n_blk = tile / p.num_m_blocks;
+        const int n0 = n_blk * p.BN;
+        int w0 = 0, h0 = 0, i0 = 0;
+        if (p.mode != 0) {
+          const int tw = m_blk % p.tiles_w;
+          const int th = (m_blk / p.tiles_w) % p.tiles_h;
+          const int tn = m_blk / (p.tiles_w * p.tiles_h);
+          w0 = tw * bw;
+          h0 = th * bh;
+          i0 = tn << p.bn_log2;
+        }
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.mode == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], it * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sb, &tmB, &full_bar[stage], it * BLOCK_K, n0);
+          } else {
+            const int tap = it / p.kc_per_tap;
+            const int c0 = (it - tap * p.kc_per_tap) * BLOCK_K;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            if (p.mode == 1) {
+              tma_load_4d(sa, &tmA, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, i0);
+            } else {
+              // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
+              const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
+              tma_load_5d(sa, &tmA, &full_bar[stage], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+            }
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + c0, n0);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, static_cast<uint32_t>(p.BN), 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STAGE_COLS;
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc = umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps) ================================
+    const int sub = warp & 3;           // TMEM sub-partition this warp may access
+    const int r = sub * 32 + lane;      // accumulator row == TMEM lane
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int n0 = n_blk * p.BN;
+      long long row;
+      int group;
+      bool valid;
+      if (p.mode == 0) {
+        row = static_cast<long long>(m_blk) * BLOCK_M + r;
+        valid = row < p.M;
+        group = p.rows_per_group > 0 ? static_cast<int>(row / p.rows_per_group) : 0;
+      } else {
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int tn = m_blk / (p.tiles_w * p.tiles_h);
+        const int dw = r & (bw - 1);
+        const int dh = (r >> p.bw_log2) & (bh - 1);
+        const int dn = r >> (p.bw_log2 + p.bh_log2);
+        const int ow = tw * bw + dw, oh = th * bh + dh, n = (tn << p.bn_log2) + dn;
+        valid = (ow < p.OW) && (oh < p.OH) && (n < p.NB);
+        row = (static_cast<long long>(n) * p.OH + oh) * p.OW + ow;
+        group = n;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STAGE_COLS;
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t a[32];
+        tmem_ld32(t_row + c, a);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (valid && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.geglu) {
+            // columns [0,16) = value, [16,32) = gate of the same 16 output features
+            const long long ocol = col0 >> 1;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf_f(v[16 + j]);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + ocol;
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(o[0], o[1]);
+            q0.y = pack_bf16x2(o[2], o[3]);
+            q0.z = pack_bf16x2(o[4], o[5]);
+            q0.w = pack_bf16x2(o[6], o[7]);
+            q1.x = pack_bf16x2(o[8], o[9]);
+            q1.y = pack_bf16x2(o[10], o[11]);
+            q1.z = pack_bf16x2(o[12], o[13]);
+            q1.w = pack_bf16x2(o[14], o[15]);
+            reinterpret_cast<uint4*>(dst)[0] = q0;
+            reinterpret_cast<uint4*>(dst)[1] = q1;
+          } else {
+            if (p.alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+            }
+            if (p.rowvec != nullptr) {
+              const float* rv = p.rowvec + static_cast<long long>(group) * p.N + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += __ldg(rv + j);
+            }
+            if (p.residual != nullptr) {
+              const __nv_bfloat16* res = p.residual + row * p.ldr + col0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (col0 + q * 8 < p.N) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(res) + q);
+                  const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                               f3 = unpack_bf16x2(u.w);
+                  v[q * 8 + 0] += f0.x;
+                  v[q * 8 + 1] += f0.y;
+                  v[q * 8 + 2] += f1.x;
+                  v[q * 8 + 3] += f1.y;
+                  v[q * 8 + 4] += f2.x;
+                  v[q * 8 + 5] += f2.y;
+                  v[q * 8 + 6] += f3.x;
+                  v[q * 8 + 7] += f3.y;
+                }
+              }
+            }
+            if (p.out_fp32) {
+              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (col0 + q * 4 < p.N)
+                  reinterpret_cast<float4*>(dst)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              }
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (col0 + q * 8 < p.N) {
+                  uint4 u;
+                  u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                  u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                  u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                  u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                  reinterpret_cast<uint4*>(dst)[q] = u;
+                }
+              }
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return ((1 << l) == v) ? l : -1;
+}
+
+// Pick the N tile: minimise waves x per-tile cost.  Per-k16 step cost is the slower of the MMA
+// (BN/2 cycles at M=128) and the shared-memory operand reads ((4 KiB + BN*32 B) / 128 B/cycle).
+static int pick_bn(int m_blocks, int N, int k_iters, int sms, int geglu) {
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn = 32; bn <= 256; bn += 32) {
+    if (bn > ((N + 31) / 32) * 32 && bn != 32) continue;
+    const int n_blocks = (N + bn - 1) / bn;
+    const long long tiles = static_cast<long long>(m_blocks) * n_blocks;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double step = fmax(bn / 2.0, 32.0 + bn / 4.0);
+    const double tile_cost = 4.0 * step * k_iters + 600.0 + bn * 6.0;  // mainloop + fill/drain + epilogue tail
+    const double cost = waves * tile_cost;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  (void)geglu;
+  return best;
+}
+
+
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int stage_bytes = A_STAGE_BYTES + p.BN * BLOCK_K * 2;
+  int stages = smem_budget / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.k_iters + 1) stages = p.k_iters + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return B200SR_ELAUNCH;
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_conv_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
+  p.bias = e.bias;
+  p.rowvec = e.rowvec;
+  p.rows_per_group = e.rows_per_group;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+  p.ldr = e.ldr;
+  p.out = e.out;
+  p.ldc = e.ldc;
+  p.out_fp32 = e.out_fp32;
+  p.geglu = e.geglu;
+  p.alpha = e.alpha;
+  if (e.out == nullptr) return B200SR_EINVAL;
+  if (e.geglu && (e.out_fp32 || e.residual != nullptr || e.rowvec != nullptr || (p.N % 32) != 0)) return B200SR_EINVAL;
+  if (p.N % 8 != 0) return B200SR_EINVAL;
+  if ((e.ldc % 8) != 0 || (e.residual != nullptr && (e.ldr % 8) != 0)) return B200SR_EINVAL;
+  return B200SR_OK;
+}
+
+int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, const EpilogueArgs& e, int force_bn,
+              cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (lda % 8) != 0) return B200SR_EINVAL;
+  GemmParams p{};
+  p.mode = 0;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.k_iters = (K + BLOCK_K - 1) / BLOCK_K;
+  p.BN = force_bn > 0 ? force_bn : pick_bn(p.num_m_blocks, N, p.k_iters, num_sms(), e.geglu);
+  if (p.BN % 32 != 0 || p.BN > 256) return B200SR_EINVAL;
+  p.num_n_blocks = (N + p.BN - 1) / p.BN;
+  int rc = fill_epilogue(p, e);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {BLOCK_K, BLOCK_M};
+    rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN)};
+    rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch(tmA, tmB, p, stream);
+}
+
+// x: NHWC bf16 [NB, H, W, Cin]; w: [Cout, 3, 3, Cin] bf16 (K = tap*Cin + c); stride 1 or 2, pad 1.
+int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride,
+                 const EpilogueArgs& e, int force_bn, cudaStream_t stream) {
+  if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin % BLOCK_K) != 0 || Cout <= 0) return B200SR_EINVAL;
+  if (stride != 1 && stride != 2) return B200SR_EINVAL;
+  if (stride == 2 && ((H | W) & 1)) return B200SR_EINVAL;
+  if (e.geglu) return B200SR_EINVAL;
+  const int OH = H / stride, OW = W / stride;
+  // tile box: bw | OW, bw*bh*bn == 128, all powers of two
+  int bw = 1;
+  while (bw * 2 <= 128 && (OW % (bw * 2)) == 0) bw *= 2;
+  int bh = 1;
+  while (bw * bh * 2 <= 128 && bh < OH) bh *= 2;
+  int bn = 128 / (bw * bh);
+  GemmParams p{};
+  p.mode = stride == 1 ? 1 : 2;
+  p.NB = NB;
+  p.OH = OH;
+  p.OW = OW;
+  p.Cin = Cin;
+  p.M = NB * OH * OW;
+  p.N = Cout;
+  p.K = 9 * Cin;
+  p.bw_log2 = ilog2_exact(bw);
+  p.bh_log2 = ilog2_exact(bh);
+  p.bn_log2 = ilog2_exact(bn);
+  p.tiles_w = OW / bw;
+  p.tiles_h = (OH + bh - 1) / bh;
+  p.tiles_n = (NB + bn - 1) / bn;
+  p.num_m_blocks = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.kc_per_tap = Cin / BLOCK_K;
+  p.k_iters = 9 * p.kc_per_tap;
+  p.BN = force_bn > 0 ? force_bn : pick_bn(p.num_m_blocks, Cout, p.k_iters, num_sms(), 0);
+  if (p.BN % 32 != 0 || p.BN > 256) return B200SR_EINVAL;
+  p.num_n_blocks = (Cout + p.BN - 1) / p.BN;
+  int rc = fill_epilogue(p, e);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  if (stride == 1) {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(NB)};
+    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
+                           static_cast<uint64_t>(H) * W * Cin * 2};
+    uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    rc = make_tmap_bf16(&tmA, x, 4, dims, strides, box);
+  } else {
+    // [NB, H/2, 2, W/2, 2*Cin]: (w parity, channel) merge into one contiguous dim of 2*Cin
+    uint64_t dims[5] = {static_cast<uint64_t>(2 * Cin), static_cast<uint64_t>(W / 2), 2,
+                        static_cast<uint64_t>(H / 2), static_cast<uint64_t>(NB)};
+    uint64_t strides[4] = {static_cast<uint64_t>(2 * Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
+                           static_cast<uint64_t>(2) * W * Cin * 2, static_cast<uint64_t>(H) * W * Cin * 2};
+    uint32_t box[5] = {BLOCK_K, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    rc = make_tmap_bf16(&tmA, x, 5, dims, strides, box);
+  }
+  if (rc) return rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(9) * Cin, static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {static_cast<uint64_t>(9) * Cin * 2};
+    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN)};
+    rc = make_tmap_bf16(&tmB, w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch(tmA, tmB, p, stream);
+}
+
+}  // namespace b200sr

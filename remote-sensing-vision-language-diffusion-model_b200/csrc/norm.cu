@@ -1,0 +1,349 @@
+// b200sr — fused GroupNorm(32)(+SiLU)(+SFT modulate) and LayerNorm for NHWC / token-major bf16
+// activations.  Memory-bound kernels: 128-bit coalesced accesses, fp32 statistics, warp-shuffle +
+// shared-memory reductions.
+//
+// Reference semantics:
+//   GroupNorm32 = nn.GroupNorm(32, C, eps=1e-5)       sgm/modules/diffusionmodules/util.py:258-276
+//   Normalize   = nn.GroupNorm(32, C, eps=1e-6)       sgm/modules/attention.py:122-125
+//   followed by nn.SiLU in ResBlock / UNet.out        openaimodel.py:254-258, :289-292, :942-944
+//   ZeroSFT modulate  GN(h) * (1 + gamma) + beta, lerp with control_scale   SR_modules.py:101-110
+//   nn.LayerNorm(C) eps 1e-5                          sgm/modules/attention.py:437-439
+//   SR3 nn.GroupNorm(32, C) + Swish                   models/sr3_model/sr3_modules/unet.py:81-92
+#include "common.cuh"
+
+namespace b200sr {
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm pass 1: per-(image, pixel-chunk, group) partial sum / sum-of-squares.
+// Thread t owns channel vector (t % C8) (8 channels, one 16-byte load per pixel) and walks
+// pixels t / C8, t / C8 + P, ... of its chunk, so consecutive threads read consecutive 16 B.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
+                int pix_per_cta, int chunks) {
+  extern __shared__ float s_red[];  // [C] sums, [C] sumsq
+  const int C8 = C >> 3;
+  const int P = blockDim.x / C8;
+  const int cv = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int n = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int p_begin = chunk * pix_per_cta;
+  const int p_end = min(HW, p_begin + pix_per_cta);
+
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (pl < P) {
+    const uint4* base = reinterpret_cast<const uint4*>(x + (static_cast<size_t>(n) * HW) * C) + cv;
+    int pix = p_begin + pl;
+    // 4 independent 16-byte loads in flight per thread
+    for (; pix + 3 * P < p_end; pix += 4 * P) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(base + static_cast<size_t>(pix + k * P) * C8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          s[2 * j] += f.x;
+          q[2 * j] += f.x * f.x;
+          s[2 * j + 1] += f.y;
+          q[2 * j + 1] += f.y * f.y;
+        }
+      }
+    }
+    for (; pix < p_end; pix += P) {
+      const uint4 u = __ldg(base + static_cast<size_t>(pix) * C8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s[2 * j] += f.x;
+        q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y;
+        q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_red[cv * 8 + j], s[j]);
+      atomicAdd(&s_red[C + cv * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += s_red[c];
+      b += s_red[C + c];
+    }
+    float* dst = partial + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm pass 2: y = (x - mean) * rstd * w + b  [-> SiLU]  [-> SFT: y * (1 + gamma) + beta,
+// lerp with the un-normalised input by control_scale].  Same thread->channel mapping as pass 1
+// so the per-channel scale/shift live in registers.
+// ------------------------------------------------------------------------------------------
+struct GnApplyArgs {
+  const __nv_bfloat16* x;
+  const float* partial;
+  const float* weight;
+  const float* bias;
+  __nv_bfloat16* y;
+  const __nv_bfloat16* sft_gamma;  // optional [N, HW, C]
+  const __nv_bfloat16* sft_beta;   // optional [N, HW, C]
+  const __nv_bfloat16* raw;        // optional un-modulated tensor for the control_scale lerp
+  float control_scale;
+  float eps;
+  int HW, C, groups, pix_per_cta, chunks_stats, silu;
+};
+
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
+  extern __shared__ float s_ab[];  // [groups] mean, [groups] rstd
+  const int C = a.C, HW = a.HW;
+  const int C8 = C >> 3;
+  const int P = blockDim.x / C8;
+  const int cv = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int n = blockIdx.y;
+  const int cpg = C / a.groups;
+
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    const float* src = a.partial + (static_cast<size_t>(n) * a.chunks_stats * a.groups + g) * 2;
+    for (int k = 0; k < a.chunks_stats; ++k) {
+      s += src[static_cast<size_t>(k) * a.groups * 2];
+      q += src[static_cast<size_t>(k) * a.groups * 2 + 1];
+    }
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_ab[g] = static_cast<float>(mean);
+    s_ab[a.groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  __syncthreads();
+  if (pl >= P) return;
+
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float w = a.weight ? a.weight[c] : 1.f;
+    const float b = a.bias ? a.bias[c] : 0.f;
+    sc[j] = s_ab[a.groups + g] * w;
+    sh[j] = b - s_ab[g] * sc[j];
+  }
+  const int p_begin = blockIdx.x * a.pix_per_cta;
+  const int p_end = min(HW, p_begin + a.pix_per_cta);
+  const size_t img = static_cast<size_t>(n) * HW;
+  const bool sft = a.sft_gamma != nullptr;
+  const float cs = a.control_scale;
+  for (int pix = p_begin + pl; pix < p_end; pix += P) {
+    const size_t off = (img + pix) * C8 + cv;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.x) + off);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[2 * j] = f.x * sc[2 * j] + sh[2 * j];
+      v[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+    }
+    if (a.silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
+    if (sft) {
+      const uint4 ug = __ldg(reinterpret_cast<const uint4*>(a.sft_gamma) + off);
+      const uint4 ub = __ldg(reinterpret_cast<const uint4*>(a.sft_beta) + off);
+      const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w};
+      const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g = unpack_bf16x2(wg[j]);
+        const float2 b = unpack_bf16x2(wb[j]);
+        v[2 * j] = v[2 * j] * (1.f + g.x) + b.x;
+        v[2 * j + 1] = v[2 * j + 1] * (1.f + g.y) + b.y;
+      }
+      if (a.raw != nullptr && cs != 1.f) {
+        const uint4 ur = __ldg(reinterpret_cast<const uint4*>(a.raw) + off);
+        const uint32_t wr[4] = {ur.x, ur.y, ur.z, ur.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 r = unpack_bf16x2(wr[j]);
+          v[2 * j] = v[2 * j] * cs + r.x * (1.f - cs);
+          v[2 * j + 1] = v[2 * j + 1] * cs + r.y * (1.f - cs);
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(a.y)[off] = o;
+  }
+}
+
+static void gn_geometry(int N, int HW, int C, int* threads, int* P, int* pix_per_cta, int* chunks) {
+  const int C8 = C / 8;
+  int p = 256 / C8;
+  if (p < 1) p = 1;
+  *P = p;
+  *threads = ((C8 * p + 31) / 32) * 32;
+  // aim for ~4 CTAs per SM across the grid, at least 4 pixels per thread row
+  int want = (4 * num_sms() + N - 1) / N;
+  if (want < 1) want = 1;
+  int ppc = (HW + want - 1) / want;
+  const int min_ppc = p * 8;
+  if (ppc < min_ppc) ppc = min_ppc;
+  if (ppc > HW) ppc = HW;
+  *pix_per_cta = ppc;
+  *chunks = (HW + ppc - 1) / ppc;
+}
+
+size_t group_norm_workspace_bytes(int N, int HW, int C, int groups) {
+  int threads, P, ppc, chunks;
+  gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
+  return static_cast<size_t>(N) * chunks * groups * 2 * sizeof(float);
+}
+
+int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int N, int HW, int C, int groups,
+                    float eps, int silu, const void* sft_gamma, const void* sft_beta, const void* raw,
+                    float control_scale, float* workspace, cudaStream_t stream) {
+  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || (C % 8) != 0 || (C % groups) != 0 || C / 8 > 1024)
+    return B200SR_EINVAL;
+  if ((sft_gamma == nullptr) != (sft_beta == nullptr)) return B200SR_EINVAL;
+  if (workspace == nullptr) return B200SR_EINVAL;
+  int threads, P, ppc, chunks;
+  gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
+  dim3 grid(chunks, N);
+  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                    workspace, HW, C, groups, ppc, chunks);
+  GnApplyArgs a;
+  a.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  a.partial = workspace;
+  a.weight = weight;
+  a.bias = bias;
+  a.y = reinterpret_cast<__nv_bfloat16*>(y);
+  a.sft_gamma = reinterpret_cast<const __nv_bfloat16*>(sft_gamma);
+  a.sft_beta = reinterpret_cast<const __nv_bfloat16*>(sft_beta);
+  a.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
+  a.control_scale = control_scale;
+  a.eps = eps;
+  a.HW = HW;
+  a.C = C;
+  a.groups = groups;
+  a.pix_per_cta = ppc;
+  a.chunks_stats = chunks;
+  a.silu = silu;
+  gn_apply_kernel<<<grid, threads, 2 * groups * sizeof(float), stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim of a token-major [M, C] bf16 matrix: one warp per row, the row
+// is held in registers (C <= 2560), two-pass mean / variance in fp32.
+// ------------------------------------------------------------------------------------------
+template <int VEC_PER_LANE>
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                  const float* __restrict__ weight, const float* __restrict__ bias, int M, int C, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int C8 = C >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
+  float v[VEC_PER_LANE][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < C8) {
+      const uint4 u = __ldg(src + vi);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < C8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+  uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * C);
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < C8) {
+      float o[8];
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight) + vi * 2);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight) + vi * 2 + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + vi * 2);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + vi * 2 + 1);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * ww[j] + bb[j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      dst[vi] = u;
+    }
+  }
+}
+
+int layer_norm(const void* x, void* y, const float* weight, const float* bias, int M, int C, float eps,
+               cudaStream_t stream) {
+  if (M <= 0 || C <= 0 || (C % 8) != 0 || C > 2560 * 2 || weight == nullptr || bias == nullptr) return B200SR_EINVAL;
+  const int rows_per_cta = 8;
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+  const int vpl = (C / 8 + 31) / 32;
+  if (vpl <= 1)
+    layer_norm_kernel<1><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+  else if (vpl <= 3)
+    layer_norm_kernel<3><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+  else if (vpl <= 5)
+    layer_norm_kernel<5><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+  else if (vpl <= 10)
+    layer_norm_kernel<10><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+  else
+    layer_norm_kernel<20><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+}  // namespace b200sr
