@@ -1,0 +1,179 @@
+"""ORACLE tooling — run in the BUILD container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+1. instantiates the real reference modules (oracle/reference_import.py), fills them with the
+   name-keyed weights of oracle/weights.py and runs them in fp32 on seeded synthetic inputs;
+2. runs the restatement (oracle/stage2.py, sampler.py, sr3.py) on the same state_dict / inputs and
+   asserts agreement (this is what pins the oracle);
+3. writes the reference outputs as small fixtures to tests/golden/*.pt (inputs and weights are
+   regenerated from seeds at test time; checksums of both are stored to detect RNG drift).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import configs, inputs, reference_import, sampler as osampler, sr3 as osr3, stage2 as ostage2, weights  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def maxdiff(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+def checksum(t: torch.Tensor):
+    t = t.double()
+    return [t.sum().item(), t.abs().sum().item()]
+
+
+def stage2(latent=16, seed=0, steps=6, threshold=0.3):
+    t0 = time.time()
+    wrapper = reference_import.stage2_modules(configs.STAGE2_UNET_TEST, configs.STAGE2_CONTROL_TEST)
+    sd = wrapper.state_dict()
+    weights.fill_(sd, seed)
+    sd = {k: v.clone() for k, v in wrapper.state_dict().items()}
+    print(f"[stage2] reference built + filled: {len(sd)} tensors, "
+          f"{sum(v.numel() for v in sd.values()) / 1e6:.0f} M params, {time.time() - t0:.1f}s")
+    x, c, uc = inputs.stage2_inputs(latent=latent, seed=1234)
+    den, smp = reference_import.stage2_sampler(device="cpu")
+    out = {"latent": latent, "seed": seed, "threshold": threshold,
+           "weight_checksum": checksum(sd["diffusion_model.input_blocks.4.1.transformer_blocks.0.attn1.to_q.weight"]),
+           "input_checksum": checksum(c["crossattn"])}
+
+    # --- single network call, CFG batch 2, fbcache_mode none / stage1+2 ---------------------------------
+    import sgm.modules.diffusionmodules.guiders as guiders
+    guider = guiders.LinearCFG(scale=4.0, scale_min=7.5)
+    sig = torch.full((1,), 14.6146)
+    xin, sin, cin = guider.prepare_inputs(x, sig, c, uc)
+    idx = den.sigma_to_idx(sin)
+    c_in = 1 / (den.sigmas[idx] ** 2 + 1) ** 0.5
+    net_x = xin * c_in.view(-1, 1, 1, 1)
+    with torch.no_grad():
+        eps_ref = wrapper(net_x, idx, cin, 1.0, "none", None)
+        info = wrapper(net_x, idx, cin, 1.0, "input_stage1", None)
+        eps_ref2 = wrapper(net_x, idx, cin, 1.0, "input_stage2", info)
+        ctrl_ref = wrapper.control_model(x=cin["control"], timesteps=idx, xt=net_x, context=cin["crossattn"],
+                                         y=cin["vector"])
+        eps_or = ostage2.control_wrapper(sd, net_x, idx, cin, 1.0)
+        ctrl_or = ostage2.glv_control(sd, "control_model.", cin["control"], idx, net_x, cin["crossattn"], cin["vector"])
+    d = maxdiff(eps_ref, eps_or)
+    print(f"[stage2] eps: |ref|max={eps_ref.abs().max():.4f} std={eps_ref.std():.4f}  oracle-vs-ref max diff {d:.3e};"
+          f" two-stage-vs-none {maxdiff(eps_ref, eps_ref2):.3e}")
+    assert d < 2e-4 * max(1.0, eps_ref.abs().max().item()), "oracle restatement disagrees with the reference"
+    for a, b in zip(ctrl_ref, ctrl_or):
+        assert maxdiff(a, b) < 2e-4 * max(1.0, a.abs().max().item())
+    out.update(net_x=net_x, idx=idx, eps=eps_ref, h_stage1=info["h"],
+               control_stats=[[t.mean().item(), t.std().item()] for t in ctrl_ref])
+
+    # --- sampler: `steps` RestoreEDMSampler steps with the first-block cache ------------------------------
+    from models.modules.DFBCache import MyCacheContext, cache_context
+
+    def ref_denoiser(inp, sigma, cc, control_scale=1.0, fbcache_mode="none", partial_info=None):
+        return den(wrapper, inp, sigma, cc, control_scale, fbcache_mode, partial_info)
+
+    oden = osampler.Denoiser()
+
+    def or_net(xx, tt, cc, cs, mode, pinfo):
+        with torch.no_grad():
+            if mode == "none":
+                return ostage2.control_wrapper(sd, xx, tt, cc, cs)
+            if mode == "input_stage1":
+                control = ostage2.glv_control(sd, "control_model.", cc["control"], tt, xx, cc["crossattn"], cc["vector"])
+                h, hs, emb = ostage2.unet_input_stage(sd, "diffusion_model.", xx, tt, cc["crossattn"], cc["vector"])
+                return {"h": h, "hs": hs, "emb": emb, "context": cc["crossattn"], "control": control}
+            return ostage2.unet_output_stage(sd, "diffusion_model.", pinfo["h"], pinfo["hs"], pinfo["emb"],
+                                             pinfo["context"], pinfo["control"], cs).float()
+
+    def or_denoiser(inp, sigma, cc, control_scale, mode, pinfo):
+        return oden(or_net, inp, sigma, cc, control_scale, mode, pinfo)
+
+    z0 = torch.randn(1, 4, latent, latent, generator=torch.Generator().manual_seed(77))
+    zr, s_in, sigmas, _, _, _ = smp.init_loop(z0.clone(), c, uc, num_steps=50)
+    osmp = osampler.RestoreSampler(device="cpu")
+    zo, os_in, osig = osmp.init_loop(z0.clone())
+    assert maxdiff(sigmas, osig) == 0.0
+    thr_r, thr_o, cache = threshold, threshold, osampler.CacheState()
+    ref_trace = []
+    with torch.no_grad(), cache_context(MyCacheContext()):
+        for i in range(steps):
+            torch.manual_seed(1000 + i)
+            zr, new_thr = smp.step(zr, i, s_in, sigmas, ref_denoiser, c, uc, x_center=None, control_scale=1.0,
+                                   threshold=thr_r)
+            ref_trace.append(("hit" if new_thr == thr_r and i > 0 else "miss", float(new_thr)))
+            thr_r = new_thr
+            torch.manual_seed(1000 + i)
+            noise = torch.randn_like(zo)
+            zo, thr_o = osmp.step(zo, i, os_in, osig, or_denoiser, c, uc, 1.0, thr_o, cache, noise)
+            print(f"[stage2] step {i}: ref thr {thr_r:.5f} oracle {osmp.trace[-1]} z diff {maxdiff(zr, zo):.3e}")
+            assert maxdiff(zr, zo) < 5e-3 and abs(thr_r - thr_o) < 1e-4
+    out.update(z0=z0, z_final=zr, trace=[list(t) for t in osmp.trace], sigmas=sigmas, steps=steps)
+    torch.save(out, os.path.join(GOLDEN, f"stage2_test_{latent}.pt"))
+    print(f"[stage2] wrote golden, total {time.time() - t0:.1f}s")
+
+
+def sr3(size=32, seed=0):
+    diff = reference_import.sr3_modules(configs.SR3_UNET, configs.SR3_SCHEDULE)
+    sd = diff.denoise_fn.state_dict()
+    weights.fill_(sd, seed)
+    sd = {k: v.clone() for k, v in diff.denoise_fn.state_dict().items()}
+    cond, noises = inputs.sr3_inputs(size=size, seed=0, steps=50)
+    level = torch.tensor([[0.73]])
+    xin = torch.cat([cond, noises[0]], dim=1)
+    with torch.no_grad():
+        e_ref = diff.denoise_fn(xin, level)
+        e_or = osr3.unet(sd, "", xin, level)
+    d = maxdiff(e_ref, e_or)
+    print(f"[sr3] unet |ref|max {e_ref.abs().max():.4f}; oracle-vs-ref {d:.3e}")
+    assert d < 1e-4 * max(1.0, e_ref.abs().max().item())
+    # full 50-step loop: the reference draws torch.randn(shape) then randn_like per step (t>0) from the global RNG
+    torch.manual_seed(5)
+    with torch.no_grad():
+        sr_ref = diff.p_sample_loop(cond, continous=False)
+    torch.manual_seed(5)
+    seq = [torch.randn(cond.shape) for _ in range(50)] + [torch.zeros_like(cond)]
+    sched = osr3.Schedule(**configs.SR3_SCHEDULE)
+    with torch.no_grad():
+        sr_or = osr3.p_sample_loop(lambda x, l: osr3.unet(sd, "", x, l), sched, cond, seq)
+    d2 = maxdiff(sr_ref, sr_or)
+    print(f"[sr3] 50-step loop oracle-vs-ref {d2:.3e}")
+    assert d2 < 1e-3
+    torch.save({"size": size, "level": level, "eps": e_ref, "sr": sr_ref, "loop_seed": 5,
+                "weight_checksum": checksum(sd["downs.1.res_block.block1.block.3.weight"])},
+               os.path.join(GOLDEN, f"sr3_{size}.pt"))
+    print("[sr3] wrote golden")
+
+
+def tables():
+    reference_import.install_stubs()
+    from sgm.modules.diffusionmodules.sampling import _sliding_windows
+    import numpy as np
+
+    den, smp = reference_import.stage2_sampler(device="cpu")
+    sig50 = smp.discretization(50, device="cpu")
+    assert maxdiff(sig50, osampler.ddpm_sigmas(50)) == 0.0
+    assert maxdiff(den.sigmas, osampler.Denoiser().sigmas) == 0.0
+    wins = _sliding_windows(256, 256, 128, 96)
+    assert wins == osampler.sliding_windows(256, 256, 128, 96)
+    # gaussian_weights in the reference allocates on 'cuda'; restate its numpy body for the fixture
+    torch.save({"sigmas50": sig50, "sigmas1000_head": den.sigmas[:8], "sigmas1000_tail": den.sigmas[-8:],
+                "windows_256_128_96": wins, "gauss_128_row64": osampler.gaussian_weights(128, 128)[64].float(),
+                "gauss_128_col64": osampler.gaussian_weights(128, 128)[:, 64].float()},
+               os.path.join(GOLDEN, "tables.pt"))
+    print("[tables] wrote golden")
+
+
+if __name__ == "__main__":
+    assert reference_import.available(), "needs /root/reference"
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_grad_enabled(False)
+    tables()
+    sr3()
+    stage2()

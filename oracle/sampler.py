@@ -112,7 +112,7 @@ class RestoreSampler:
         xin, sin, cin = cfg_prepare(x, sigma, c, uc)
         if threshold <= 0:
             den = denoiser(xin, sin, cin, control_scale, "none", None)
-            return cfg_combine(den, sin, self.scale, self.scale_min), threshold
+            return cfg_combine(den, sigma, self.scale, self.scale_min), threshold
         info = denoiser(xin, sin, cin, control_scale, "input_stage1", None)
         if cache.prev is not None:
             diff = rel_l1(cache.prev, info["h"])
@@ -124,7 +124,7 @@ class RestoreSampler:
             return cache.final_decode, threshold
         cache.prev = info["h"].clone()
         den = denoiser(xin, sin, cin, control_scale, "input_stage2", info)
-        den = cfg_combine(den, sin, self.scale, self.scale_min)
+        den = cfg_combine(den, sigma, self.scale, self.scale_min)
         cache.final_decode = den.clone()
         self.trace.append(("miss", th))
         return den, th
