@@ -48,6 +48,7 @@ typedef struct b200sr_epilogue {
   int32_t out_fp32;
   int32_t geglu;
   float alpha;
+  int32_t act;              /* 0 = none, 1 = SiLU applied to the final value (ZeroSFT mlp_shared, SR_modules.py:75-78) */
 } b200sr_epilogue;
 
 /* D = A[M,K] * W[N,K]^T with fused epilogue; bf16 operands, fp32 accumulate (tcgen05 / TMEM).

@@ -170,10 +170,35 @@ def tables():
     print("[tables] wrote golden")
 
 
+def keys():
+    """state_dict key -> shape of the FULL reference configuration (meta device, no memory)."""
+    import json
+
+    with torch.device("meta"):
+        wrapper = reference_import.stage2_modules(configs.STAGE2_UNET, configs.STAGE2_CONTROL)
+        diff = reference_import.sr3_modules(configs.SR3_UNET, configs.SR3_SCHEDULE) if False else None
+    with open(os.path.join(GOLDEN, "stage2_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in wrapper.state_dict().items()}, f, indent=0, sort_keys=True)
+    reference_import.install_stubs()
+    from models.sr3_model.sr3_modules.unet import UNet
+
+    cfg = configs.SR3_UNET
+    with torch.device("meta"):
+        net = UNet(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
+                   inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+                   res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_size=cfg["image_size"])
+    with open(os.path.join(GOLDEN, "sr3_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in net.state_dict().items()}, f, indent=0, sort_keys=True)
+    print("[keys] wrote golden")
+
+
 if __name__ == "__main__":
     assert reference_import.available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_grad_enabled(False)
+    keys()
+    if "--keys-only" in sys.argv:
+        sys.exit(0)
     tables()
     sr3()
     stage2()

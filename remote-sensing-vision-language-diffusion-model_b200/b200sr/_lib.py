@@ -31,6 +31,7 @@ class Epilogue(C.Structure):
         ("out_fp32", c_int),
         ("geglu", c_int),
         ("alpha", c_float),
+        ("act", c_int),
     ]
 
 

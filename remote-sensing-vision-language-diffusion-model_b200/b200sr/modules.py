@@ -1,0 +1,748 @@
+"""Drop-in stage-2 denoiser modules: same constructor arguments, ``forward`` signatures and
+``state_dict`` keys as the reference classes, with the compute routed to the sm_100a kernels.
+
+Mirrored reference classes (file:line relative to the reference root):
+  TimestepBlock / TimestepEmbedSequential   sgm/modules/diffusionmodules/openaimodel.py:63-99
+  Upsample / Downsample / ResBlock          openaimodel.py:102-145, :164-204, :207-350
+  UNetModel                                 openaimodel.py:500-1007
+  GEGLU / FeedForward / CrossAttention      sgm/modules/attention.py:84-110, :196-285
+  BasicTransformerBlock / SpatialTransformer  attention.py:376-486, :533-635
+  ZeroSFT / ZeroCrossAttn / GLVControl / LightGLVUNet   models/modules/SR_modules.py:59-149, :152-537, :540-883
+  ControlWrapper                            sgm/modules/diffusionmodules/wrappers.py:68-110
+
+Tensor convention at every public ``forward``: images are NCHW-*shaped* tensors.  fp32 / arbitrary
+inputs are converted once; everything these modules return is a bf16 tensor whose memory is
+channels-last (``y.permute(0, 2, 3, 1)`` is contiguous), so chained modules exchange NHWC views
+without copies, while any torch consumer still sees an ordinary ``[N, C, H, W]`` tensor.  Tokens
+are ``[B, T, C]`` bf16.  Parameters remain ordinary fp32 ``nn.Parameter``s under the reference's
+names; bf16 K-major copies for the tensor cores are packed lazily and re-packed when a parameter
+changes (``load_state_dict`` / ``.to()``).
+
+Numerics follow the reference's autocast policy: bf16 operands, fp32
+accumulation, fp32 normalisation statistics and softmax; activations are stored in bf16.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def exists(x):
+    return x is not None
+
+
+def zero_module(module: nn.Module) -> nn.Module:
+    """util.py:233-239."""
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-shaped tensor -> contiguous [N, H, W, C] bf16 (zero-copy for our own outputs)."""
+    if x.dim() != 4:
+        raise ValueError(f"expected a 4-D NCHW tensor, got {tuple(x.shape)}")
+    v = x.permute(0, 2, 3, 1)
+    if x.dtype == bf16 and v.is_contiguous():
+        return v
+    if x.dtype == torch.float32 and x.is_contiguous():
+        return ops.nchw_to_nhwc_bf16(x)
+    return v.to(bf16).contiguous()  # exotic layouts / dtypes: plain layout plumbing
+
+
+def from_nhwc(y: torch.Tensor) -> torch.Tensor:
+    return y.permute(0, 3, 1, 2)
+
+
+def tokens_bf16(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype == bf16 and x.is_contiguous():
+        return x
+    if x.dtype == torch.float32:
+        return ops.cast_bf16(x.contiguous())
+    return x.to(bf16).contiguous()
+
+
+class Packed:
+    """Mixin: lazily packed (bf16 / fused) copies of parameters, invalidated when they change."""
+
+    def _pk(self, name: str, params, fn):
+        cache = self.__dict__.setdefault("_pk_cache", {})
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+        hit = cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, fn(*params))
+            cache[name] = hit
+        return hit[1]
+
+
+_F32 = lambda p: p.detach().float().contiguous()  # noqa: E731
+
+
+def _silu_of(emb: torch.Tensor) -> torch.Tensor:
+    """SiLU(emb), shared by every ResBlock of one forward (openaimodel.py:281-283)."""
+    # The result rides on the emb tensor *object* (never keyed by address: the caching allocator
+    # hands the same address to the next step's emb).
+    s = getattr(emb, "_b200sr_silu", None)
+    if s is None:
+        s = ops.silu(tokens_bf16(emb))
+        try:
+            emb._b200sr_silu = s
+        except Exception:  # pragma: no cover - exotic tensor subclasses
+            pass
+    return s
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    """util.py:206-230 (cos | sin); returns bf16 [B, dim]."""
+    return ops.sinusoid_embedding(timesteps, dim, max_period, sin_first=False)
+
+
+class GroupNorm32(nn.GroupNorm):
+    """util.py:258-276 — parameter container; the fused kernel is invoked by the owning block."""
+
+
+def normalization(channels: int) -> nn.GroupNorm:
+    return GroupNorm32(32, channels)
+
+
+def _gn(norm: nn.GroupNorm, x_nhwc: torch.Tensor, silu: bool = False, **kw) -> torch.Tensor:
+    return ops.group_norm(x_nhwc, norm.weight, norm.bias, groups=norm.num_groups, eps=norm.eps, silu=silu, **kw)
+
+
+def _conv3x3(holder: Packed, name: str, conv: nn.Conv2d, x_nhwc: torch.Tensor, **kw) -> torch.Tensor:
+    w = holder._pk(name + ".w", (conv.weight,), ops.pack_conv3x3)
+    b = holder._pk(name + ".b", (conv.bias,), _F32) if conv.bias is not None else None
+    return ops.conv3x3(x_nhwc, w, b, **kw)
+
+
+def _linear(holder: Packed, name: str, lin, x: torch.Tensor, **kw) -> torch.Tensor:
+    w = holder._pk(name + ".w", (lin.weight,), ops.pack_linear)
+    b = holder._pk(name + ".b", (lin.bias,), _F32) if lin.bias is not None else None
+    return ops.gemm(x, w, b, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# openaimodel.py blocks
+# ------------------------------------------------------------------------------------------------
+class TimestepBlock(nn.Module):
+    """openaimodel.py:63-72."""
+
+
+class Upsample(nn.Module, Packed):
+    """openaimodel.py:102-145: nearest x2 (+ 3x3 conv)."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1, third_up=False):
+        super().__init__()
+        assert dims == 2 and padding == 1
+        self.channels, self.out_channels, self.use_conv, self.dims = channels, out_channels or channels, use_conv, dims
+        if use_conv:
+            self.conv = nn.Conv2d(self.channels, self.out_channels, 3, padding=padding)
+
+    def forward_nhwc(self, x):
+        assert x.shape[-1] == self.channels
+        x = ops.upsample2x(x)
+        return _conv3x3(self, "conv", self.conv, x) if self.use_conv else x
+
+    def forward(self, x):
+        return from_nhwc(self.forward_nhwc(to_nhwc(x)))
+
+
+class Downsample(nn.Module, Packed):
+    """openaimodel.py:164-204: 3x3 conv, stride 2, pad 1."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1, third_down=False):
+        super().__init__()
+        assert dims == 2 and use_conv and padding == 1, "only the learned stride-2 convolution is on the hot path"
+        self.channels, self.out_channels, self.use_conv, self.dims = channels, out_channels or channels, use_conv, dims
+        self.op = nn.Conv2d(self.channels, self.out_channels, 3, stride=2, padding=padding)
+
+    def forward_nhwc(self, x):
+        assert x.shape[-1] == self.channels
+        return _conv3x3(self, "op", self.op, x, stride=2)
+
+    def forward(self, x):
+        return from_nhwc(self.forward_nhwc(to_nhwc(x)))
+
+
+class ResBlock(TimestepBlock, Packed):
+    """openaimodel.py:207-350 (the configuration the YAML selects: no up/down, additive emb)."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, use_scale_shift_norm=False,
+                 dims=2, use_checkpoint=False, up=False, down=False, kernel_size=3, exchange_temb_dims=False,
+                 skip_t_emb=False):
+        super().__init__()
+        assert dims == 2 and kernel_size == 3 and not (up or down or use_scale_shift_norm or skip_t_emb or use_conv)
+        self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
+        self.out_channels = out_channels or channels
+        self.use_checkpoint, self.use_scale_shift_norm = use_checkpoint, use_scale_shift_norm
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.updown = False
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+
+    def forward_nhwc(self, x, emb):
+        # emb add is fused into conv1's epilogue, the skip add into conv2's (openaimodel.py:337-350)
+        emb_out = _linear(self, "emb", self.emb_layers[1], _silu_of(emb), out_fp32=True)
+        h = _gn(self.in_layers[0], x, silu=True)
+        h = _conv3x3(self, "conv1", self.in_layers[2], h, rowvec=emb_out)
+        h = _gn(self.out_layers[0], h, silu=True)
+        skip = x if isinstance(self.skip_connection, nn.Identity) else _linear(self, "skip", self.skip_connection, x)
+        return _conv3x3(self, "conv2", self.out_layers[3], h, residual=skip)
+
+    def forward(self, x, emb):
+        return from_nhwc(self.forward_nhwc(to_nhwc(x), emb))
+
+
+# ------------------------------------------------------------------------------------------------
+# attention.py blocks
+# ------------------------------------------------------------------------------------------------
+class GEGLU(nn.Module, Packed):
+    """attention.py:84-91; value * gelu(gate) fused into the projection's epilogue."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        w, b = self._pk("proj", (self.proj.weight, self.proj.bias), ops.pack_geglu)
+        return ops.gemm(tokens_bf16(x), w, b, geglu=True)
+
+
+class FeedForward(nn.Module, Packed):
+    """attention.py:94-110 (glu=True on this path)."""
+
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.0):
+        super().__init__()
+        assert glu, "only the gated feed-forward is on the hot path"
+        inner_dim = int(dim * mult)
+        dim_out = dim_out or dim
+        self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
+
+    def forward(self, x, residual: Optional[torch.Tensor] = None):
+        return _linear(self, "out", self.net[2], self.net[0](x), residual=residual)
+
+
+class CrossAttention(nn.Module, Packed):
+    """attention.py:196-285: q/k/v without bias, heads of 64, SDPA scale 1/8, out Linear with bias.
+    Self-attention runs one fused QKV GEMM whose output the attention kernel reads in place."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.0, backend=None):
+        super().__init__()
+        assert dim_head == 64, "the tcgen05 attention kernel is specialised for head_dim 64"
+        inner_dim = dim_head * heads
+        context_dim = context_dim or query_dim
+        self.scale, self.heads = dim_head**-0.5, heads
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+        self.backend = backend
+
+    def attend(self, x, context=None):
+        """x: [B, T, C] bf16 -> attention output before to_out, [B, T, inner]."""
+        inner = self.to_q.weight.shape[0]
+        if context is None:
+            w = self._pk("qkv", (self.to_q.weight, self.to_k.weight, self.to_v.weight),
+                         lambda q, k, v: torch.cat([q, k, v], 0).to(bf16).contiguous())
+            qkv = ops.gemm(x, w)
+            return ops.attention(qkv, qkv, qkv, self.heads, q_col=0, k_col=inner, v_col=2 * inner, scale=self.scale)
+        q = _linear(self, "q", self.to_q, x)
+        wkv = self._pk("kv", (self.to_k.weight, self.to_v.weight), lambda k, v: torch.cat([k, v], 0).to(bf16).contiguous())
+        kv = ops.gemm(context, wkv)
+        return ops.attention(q, kv, kv, self.heads, q_col=0, k_col=0, v_col=inner, scale=self.scale)
+
+    def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
+                residual: Optional[torch.Tensor] = None, alpha: float = 1.0):
+        if mask is not None or additional_tokens is not None or n_times_crossframe_attn_in_self:
+            raise NotImplementedError("masks / additional tokens / cross-frame attention are not on the hot path")
+        x = tokens_bf16(x)
+        ctx = tokens_bf16(context) if context is not None else None
+        return _linear(self, "out", self.to_out[0], self.attend(x, ctx), residual=residual, alpha=alpha)
+
+
+MemoryEfficientCrossAttention = CrossAttention  # attention.py:288-373 computes the same function
+
+
+class BasicTransformerBlock(nn.Module):
+    """attention.py:376-486; the three residual adds are fused into the producing GEMMs."""
+
+    def __init__(self, dim, n_heads, d_head, dropout=0.0, context_dim=None, gated_ff=True, checkpoint=True,
+                 disable_self_attn=False, attn_mode="softmax", sdp_backend=None):
+        super().__init__()
+        self.disable_self_attn = disable_self_attn
+        self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout,
+                                    context_dim=context_dim if disable_self_attn else None)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
+                                    dropout=dropout)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.checkpoint = checkpoint
+
+    @staticmethod
+    def _ln(norm: nn.LayerNorm, x):
+        return ops.layer_norm(x, norm.weight, norm.bias, norm.eps)
+
+    def forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0):
+        x = tokens_bf16(x)
+        x = self.attn1(self._ln(self.norm1, x), context=context if self.disable_self_attn else None, residual=x)
+        x = self.attn2(self._ln(self.norm2, x), context=context, residual=x)
+        return self.ff(self._ln(self.norm3, x), residual=x)
+
+
+class SpatialTransformer(nn.Module, Packed):
+    """attention.py:533-635 with use_linear=True.  NHWC pixels *are* the token matrix, so both
+    rearranges are free; proj_out's epilogue adds the block input."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0.0, context_dim=None, disable_self_attn=False,
+                 use_linear=False, attn_type="softmax", use_checkpoint=True, sdp_backend=None):
+        super().__init__()
+        assert use_linear, "the YAML selects use_linear_in_transformer=True"
+        if exists(context_dim) and not isinstance(context_dim, (list, tuple)):
+            context_dim = [context_dim]
+        if exists(context_dim):
+            context_dim = list(context_dim)
+            if depth != len(context_dim):
+                assert all(c == context_dim[0] for c in context_dim)
+                context_dim = depth * [context_dim[0]]
+        else:
+            context_dim = [None] * depth
+        self.in_channels = in_channels
+        inner_dim = n_heads * d_head
+        self.norm = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner_dim)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
+                                  disable_self_attn=disable_self_attn, attn_mode=attn_type, checkpoint=use_checkpoint)
+            for d in range(depth)])
+        self.proj_out = zero_module(nn.Linear(inner_dim, in_channels))
+        self.use_linear = use_linear
+
+    def forward_nhwc(self, x, context=None):
+        if not isinstance(context, list):
+            context = [context]
+        context = [tokens_bf16(c) if c is not None else None for c in context]
+        b, h, w, c = x.shape
+        t = _gn(self.norm, x).view(b, h * w, c)
+        t = _linear(self, "proj_in", self.proj_in, t)
+        for i, block in enumerate(self.transformer_blocks):
+            t = block(t, context=context[i if len(context) > 1 else 0])
+        t = _linear(self, "proj_out", self.proj_out, t, residual=x.view(b, h * w, c))
+        return t.view(b, h, w, c)
+
+    def forward(self, x, context=None):
+        return from_nhwc(self.forward_nhwc(to_nhwc(x), context))
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """openaimodel.py:75-99."""
+
+    def forward_nhwc(self, x, emb, context=None):
+        for layer in self:
+            if isinstance(layer, TimestepBlock):
+                x = layer.forward_nhwc(x, emb)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer.forward_nhwc(x, context)
+            elif isinstance(layer, nn.Conv2d):
+                x = _stem_conv(layer, x)
+            else:
+                x = layer.forward_nhwc(x)
+        return x
+
+    def forward(self, x, emb, context=None, **unused):
+        return from_nhwc(self.forward_nhwc(to_nhwc(x), emb, context))
+
+
+def _stem_conv(conv: nn.Conv2d, x_nhwc: torch.Tensor, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """latent (<= 8 channels) -> features: direct convolution kernel (input_blocks.0.0, input_hint_block.0)."""
+    cache = conv.__dict__.setdefault("_pk_cache", {})
+    key = (conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)
+    if cache.get("key") != key:
+        with torch.no_grad():
+            cache["key"], cache["w"], cache["b"] = key, ops.pack_conv3x3(conv.weight), _F32(conv.bias)
+    return ops.conv3x3_small(x_nhwc, cache["w"], cache["b"], addend=addend)
+
+
+# ------------------------------------------------------------------------------------------------
+# UNetModel (constructor only builds what the YAML configuration uses)
+# ------------------------------------------------------------------------------------------------
+class UNetModel(nn.Module, Packed):
+    """openaimodel.py:500-1007 for use_spatial_transformer=True, dims=2, conv resampling,
+    num_classes in {None, "sequential"}.  Produces the reference's module tree / state_dict keys."""
+
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
+                 use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
+                 resblock_updown=False, use_new_attention_order=False, use_spatial_transformer=False,
+                 transformer_depth=1, context_dim=None, n_embed=None, legacy=True, disable_self_attentions=None,
+                 num_attention_blocks=None, disable_middle_self_attn=False, use_linear_in_transformer=False,
+                 spatial_transformer_attn_type="softmax", adm_in_channels=None, use_fairscale_checkpoint=False,
+                 offload_to_cpu=False, transformer_depth_middle=None, _build_output_blocks=True):
+        super().__init__()
+        assert use_spatial_transformer and context_dim is not None and dims == 2 and conv_resample
+        assert not resblock_updown and not use_scale_shift_norm and n_embed is None
+        assert num_head_channels != -1 or num_heads != -1
+        if isinstance(context_dim, (list, tuple)) or type(context_dim).__name__ == "ListConfig":
+            context_dim = list(context_dim)
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        if isinstance(transformer_depth, int):
+            transformer_depth = len(channel_mult) * [transformer_depth]
+        transformer_depth = list(transformer_depth)
+        transformer_depth_middle = transformer_depth[-1] if transformer_depth_middle is None else transformer_depth_middle
+        if isinstance(num_res_blocks, int):
+            self.num_res_blocks = len(channel_mult) * [num_res_blocks]
+        else:
+            if len(num_res_blocks) != len(channel_mult):
+                raise ValueError("provide num_res_blocks either as an int (globally constant) or as a list/tuple "
+                                 "(per-level) with the same length as channel_mult")
+            self.num_res_blocks = list(num_res_blocks)
+        self.attention_resolutions, self.dropout, self.channel_mult = attention_resolutions, dropout, channel_mult
+        self.conv_resample, self.num_classes, self.use_checkpoint = conv_resample, num_classes, use_checkpoint
+        self.num_heads, self.num_head_channels = num_heads, num_head_channels
+        self.num_heads_upsample = num_heads if num_heads_upsample == -1 else num_heads_upsample
+        self.predict_codebook_ids = False
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(),
+                                        nn.Linear(time_embed_dim, time_embed_dim))
+        if num_classes is not None:
+            if num_classes != "sequential":
+                raise ValueError("only num_classes='sequential' (SDXL vector conditioning) is on the hot path")
+            assert adm_in_channels is not None
+            self.label_emb = nn.Sequential(nn.Sequential(nn.Linear(adm_in_channels, time_embed_dim), nn.SiLU(),
+                                                         nn.Linear(time_embed_dim, time_embed_dim)))
+
+        def heads_for(ch):
+            if num_head_channels == -1:
+                return num_heads, ch // num_heads
+            return ch // num_head_channels, num_head_channels
+
+        def transformer(ch, depth, level=None, middle=False):
+            nh, dh = heads_for(ch)
+            if legacy:
+                dh = ch // nh
+            disabled = disable_middle_self_attn if middle else (
+                disable_self_attentions[level] if exists(disable_self_attentions) else False)
+            return SpatialTransformer(ch, nh, dh, depth=depth, context_dim=context_dim, disable_self_attn=disabled,
+                                      use_linear=use_linear_in_transformer, attn_type=spatial_transformer_attn_type,
+                                      use_checkpoint=use_checkpoint)
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        input_block_chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for nr in range(self.num_res_blocks[level]):
+                layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels, dims=dims,
+                                   use_checkpoint=use_checkpoint)]
+                ch = mult * model_channels
+                if ds in attention_resolutions and (not exists(num_attention_blocks) or nr < num_attention_blocks[level]):
+                    layers.append(transformer(ch, transformer_depth[level], level))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
+                input_block_chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint),
+            transformer(ch, transformer_depth_middle, middle=True),
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint))
+        if not _build_output_blocks:
+            return
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(self.num_res_blocks[level] + 1):
+                ich = input_block_chans.pop()
+                layers = [ResBlock(ch + ich, time_embed_dim, dropout, out_channels=model_channels * mult, dims=dims,
+                                   use_checkpoint=use_checkpoint)]
+                ch = model_channels * mult
+                if ds in attention_resolutions and (not exists(num_attention_blocks) or i < num_attention_blocks[level]):
+                    layers.append(transformer(ch, transformer_depth[level], level))
+                if level and i == self.num_res_blocks[level]:
+                    layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(),
+                                 zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
+
+    # -- shared pieces ------------------------------------------------------------------------
+    def _embed(self, timesteps, y):
+        """time_embed(t_emb) + label_emb(y) -> bf16 [B, 4*model_channels] (openaimodel.py:987-992)."""
+        t_emb = timestep_embedding(timesteps, self.model_channels)
+        h = _linear(self, "te0", self.time_embed[0], t_emb, act=1)
+        if self.num_classes is None:
+            return _linear(self, "te2", self.time_embed[2], h)
+        emb_t = _linear(self, "te2", self.time_embed[2], h)
+        l = _linear(self, "le0", self.label_emb[0][0], tokens_bf16(y), act=1)
+        return _linear(self, "le2", self.label_emb[0][2], l, residual=emb_t)
+
+    def _out_nchw_f32(self, h_nhwc):
+        """self.out: GN32 + SiLU + 3x3 conv to the latent channels, written as fp32 NCHW (openaimodel.py:941-947)."""
+        h = _gn(self.out[0], h_nhwc, silu=True)
+        conv = self.out[2]
+        w = self._pk("out.w", (conv.weight,), ops.pack_conv3x3)
+        b = self._pk("out.b", (conv.bias,), _F32)
+        return ops.conv3x3_small(h, w, b, out_nchw_f32=True)
+
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """openaimodel.py:973-1007 (plain UNet, skip connections by concatenation)."""
+        assert (y is not None) == (self.num_classes is not None)
+        emb = self._embed(timesteps, y)
+        ctx = tokens_bf16(context)
+        h, hs = to_nhwc(x), []
+        for module in self.input_blocks:
+            h = module.forward_nhwc(h, emb, ctx)
+            hs.append(h)
+        h = self.middle_block.forward_nhwc(h, emb, ctx)
+        for module in self.output_blocks:
+            h = module.forward_nhwc(ops.concat_add(h, hs.pop()), emb, ctx)
+        return self._out_nchw_f32(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# SR_modules.py: adapters, control net, adapted UNet
+# ------------------------------------------------------------------------------------------------
+class ZeroSFT(nn.Module, Packed):
+    """SR_modules.py:59-110.  zero_conv's epilogue adds the skip feature; the concat, GroupNorm,
+    (1 + gamma) / beta modulation and control_scale lerp run as one normalisation kernel."""
+
+    def __init__(self, label_nc, norm_nc, concat_channels=0, norm=True, mask=False):
+        super().__init__()
+        assert norm
+        self.norm = norm
+        self.param_free_norm = normalization(norm_nc + concat_channels)
+        nhidden = 128
+        self.mlp_shared = nn.Sequential(nn.Conv2d(label_nc, nhidden, kernel_size=3, padding=1), nn.SiLU())
+        self.zero_mul = zero_module(nn.Conv2d(nhidden, norm_nc + concat_channels, kernel_size=3, padding=1))
+        self.zero_add = zero_module(nn.Conv2d(nhidden, norm_nc + concat_channels, kernel_size=3, padding=1))
+        self.zero_conv = zero_module(nn.Conv2d(label_nc, norm_nc, 1, 1, 0))
+        self.pre_concat = bool(concat_channels != 0)
+        self.mask = mask
+
+    def forward_nhwc(self, c, h, h_ori=None, control_scale=1):
+        assert self.mask is False
+        cat = h_ori is not None and self.pre_concat
+        if h_ori is not None and not self.pre_concat:
+            raise NotImplementedError("post-concat ZeroSFT is not used by LightGLVUNet")
+        control_scale = float(control_scale)
+        hz = _linear(self, "zero_conv", self.zero_conv, c, residual=h)  # h + zero_conv(c)
+        hc = ops.concat_add(h_ori, hz) if cat else hz
+        actv = _conv3x3(self, "mlp", self.mlp_shared[0], c, act=1)
+        gamma = _conv3x3(self, "mul", self.zero_mul, actv)
+        beta = _conv3x3(self, "add", self.zero_add, actv)
+        raw = None
+        if control_scale != 1.0:
+            raw = ops.concat_add(h_ori, h) if cat else h
+        return _gn(self.param_free_norm, hc, sft_gamma=gamma, sft_beta=beta, raw=raw, control_scale=control_scale)
+
+    def forward(self, c, h, h_ori=None, control_scale=1):
+        return from_nhwc(self.forward_nhwc(to_nhwc(c), to_nhwc(h), None if h_ori is None else to_nhwc(h_ori),
+                                           control_scale))
+
+
+class ZeroCrossAttn(nn.Module, Packed):
+    """SR_modules.py:113-149: x + CrossAttention(GN(x), GN(context)) * control_scale."""
+
+    def __init__(self, context_dim, query_dim, zero_out=True, mask=False):
+        super().__init__()
+        self.attn = CrossAttention(query_dim=query_dim, context_dim=context_dim, heads=query_dim // 64, dim_head=64)
+        self.norm1 = normalization(query_dim)
+        self.norm2 = normalization(context_dim)
+        self.mask = mask
+
+    def forward_nhwc(self, context, x, control_scale=1):
+        assert self.mask is False
+        b, h, w, c = x.shape
+        xt = _gn(self.norm1, x).view(b, h * w, c)
+        ct = _gn(self.norm2, context).view(b, h * w, context.shape[-1])
+        out = self.attn(xt, ct, residual=x.view(b, h * w, c), alpha=float(control_scale))
+        return out.view(b, h, w, c)
+
+    def forward(self, context, x, control_scale=1):
+        return from_nhwc(self.forward_nhwc(to_nhwc(context), to_nhwc(x), control_scale))
+
+
+class GLVControl(UNetModel):
+    """SR_modules.py:152-537: encoder half + middle block of the SDXL UNet run on the noisy latent,
+    with the LQ latent injected through a (zero-initialised) hint convolution after the stem."""
+
+    def __init__(self, *args, input_upscale=1, **kwargs):
+        super().__init__(*args, _build_output_blocks=False, **kwargs)
+        assert input_upscale == 1
+        self.input_upscale = input_upscale
+        self.input_hint_block = TimestepEmbedSequential(
+            zero_module(nn.Conv2d(self.in_channels, self.model_channels, 3, padding=1)))
+
+    def forward_nhwc(self, x, timesteps, xt, context, y) -> List[torch.Tensor]:
+        emb = self._embed(timesteps, y)
+        hint = _stem_conv(self.input_hint_block[0], x)
+        hs = []
+        h = _stem_conv(self.input_blocks[0][0], xt, addend=hint)  # h = conv(xt); h += guided_hint
+        hs.append(h)
+        for module in list(self.input_blocks)[1:]:
+            h = module.forward_nhwc(h, emb, context)
+            hs.append(h)
+        hs.append(self.middle_block.forward_nhwc(h, emb, context))
+        return hs
+
+    def forward(self, x, timesteps, xt, context=None, y=None, **kwargs):
+        assert (y is not None) == (self.num_classes is not None)
+        hs = self.forward_nhwc(to_nhwc(x), timesteps, to_nhwc(xt), tokens_bf16(context), y)
+        return [from_nhwc(h) for h in hs]
+
+
+class LightGLVUNet(UNetModel):
+    """SR_modules.py:540-883: SDXL UNet whose skip concatenations are replaced by ZeroSFT adapters fed
+    with the control features, plus two ZeroCrossAttn adapters before the upsamplers; fbcache modes
+    "none", "input_stage1", "input_stage2" (the ones RestoreEDMSampler.fb_mode selects, sampling.py:543)."""
+
+    def __init__(self, mode="", project_type="ZeroSFT", project_channel_scale=1, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if mode == "XL-base":
+            cond_output_channels = [320] * 4 + [640] * 3 + [1280] * 3
+            project_channels = [160] * 4 + [320] * 3 + [640] * 3
+            concat_channels = [320] * 2 + [640] * 3 + [1280] * 4 + [0]
+            cross_attn_insert_idx = [6, 3]
+            self.progressive_mask_nums = [0, 3, 7, 11]
+        elif mode == "XL-refine":
+            cond_output_channels = [384] * 4 + [768] * 3 + [1536] * 6
+            project_channels = [192] * 4 + [384] * 3 + [768] * 6
+            concat_channels = [384] * 2 + [768] * 3 + [1536] * 7 + [0]
+            cross_attn_insert_idx = [9, 6, 3]
+            self.progressive_mask_nums = [0, 3, 6, 10, 14]
+        else:
+            raise NotImplementedError
+        project_channels = [int(c * project_channel_scale) for c in project_channels]
+        self.cache_threshold = 0.1
+        self.project_modules = nn.ModuleList()
+        for i in range(len(cond_output_channels)):
+            if project_type == "ZeroSFT":
+                self.project_modules.append(ZeroSFT(project_channels[i], cond_output_channels[i],
+                                                    concat_channels=concat_channels[i]))
+            elif project_type == "ZeroCrossAttn":
+                self.project_modules.append(ZeroCrossAttn(cond_output_channels[i], project_channels[i]))
+            else:
+                raise NotImplementedError
+        for i in cross_attn_insert_idx:
+            self.project_modules.insert(i, ZeroCrossAttn(cond_output_channels[i], concat_channels[i]))
+
+    def step_progressive_mask(self):
+        if len(self.progressive_mask_nums) > 0:
+            mask_num = self.progressive_mask_nums.pop()
+            for i in range(len(self.project_modules)):
+                self.project_modules[i].mask = i < mask_num
+
+    # -- the two halves of the network --------------------------------------------------------
+    def _input_stage(self, x, emb, context):
+        hs, h = [], x
+        for module in self.input_blocks:
+            if isinstance(module[0], nn.Conv2d):
+                h = _stem_conv(module[0], h)
+            else:
+                h = module.forward_nhwc(h, emb, context)
+            hs.append(h)
+        return h, hs
+
+    def _output_stage(self, h, hs, emb, context, control, control_scale):
+        hs = list(hs)
+        adapter_idx = len(self.project_modules) - 1
+        control_idx = len(control) - 1
+        h = self.middle_block.forward_nhwc(h, emb, context)
+        h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], h, control_scale=control_scale)
+        adapter_idx -= 1
+        control_idx -= 1
+        for module in self.output_blocks:
+            _h = hs.pop()
+            h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], _h, h, control_scale=control_scale)
+            adapter_idx -= 1
+            if len(module) == 3:
+                assert isinstance(module[2], Upsample)
+                h = module[0].forward_nhwc(h, emb)
+                h = module[1].forward_nhwc(h, context)
+                h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], h, control_scale=control_scale)
+                adapter_idx -= 1
+                h = module[2].forward_nhwc(h)
+            else:
+                h = module.forward_nhwc(h, emb, context)
+            control_idx -= 1
+        return self._out_nchw_f32(h)
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, control=None, control_scale=1.0, fbcache_mode="none",
+                partial_info=None, **kwargs):
+        assert (y is not None) == (self.num_classes is not None)
+        if fbcache_mode in ("none", "input_stage1"):
+            emb = self._embed(timesteps, y)
+            ctx = tokens_bf16(context)
+            ctrl = [to_nhwc(c) for c in control]
+            h, hs = self._input_stage(to_nhwc(x), emb, ctx)
+            if fbcache_mode == "input_stage1":
+                return {"mode": "input", "h": from_nhwc(h), "hs": [from_nhwc(t) for t in hs], "emb": emb,
+                        "context": ctx, "control": [from_nhwc(c) for c in ctrl],
+                        "adapter_idx": len(self.project_modules) - 1, "control_idx": len(ctrl) - 1}
+            return self._output_stage(h, hs, emb, ctx, ctrl, control_scale)
+        if fbcache_mode == "input_stage2":
+            if partial_info is None or partial_info.get("mode", "") != "input":
+                raise ValueError("input_stage2 requires partial_info from input_stage1")
+            return self._output_stage(to_nhwc(partial_info["h"]), [to_nhwc(t) for t in partial_info["hs"]],
+                                      partial_info["emb"], tokens_bf16(partial_info["context"]),
+                                      [to_nhwc(c) for c in partial_info["control"]], control_scale)
+        if fbcache_mode in ("middle_stage1", "middle_stage2", "output_stage1", "output_stage2"):
+            raise NotImplementedError(f"fbcache_mode={fbcache_mode}: RestoreEDMSampler.fb_mode is fixed to 'input_stage' "
+                                      "(sampling.py:543); the middle/output variants are not on the hot path")
+        raise ValueError(f"Unknown fbcache_mode={fbcache_mode}")
+
+
+class ControlWrapper(nn.Module):
+    """wrappers.py:68-110.  `dtype` is kept for interface compatibility (SR_model.py:41 sets it); the
+    kernels always compute bf16 x bf16 -> fp32.  Differences from the reference, both semantics-
+    preserving: no torch.autocast context is needed, and in "input_stage2" the control net is not
+    re-run (the reference recomputes it and then uses the copy stored in partial_info, SR_modules.py:694)."""
+
+    def __init__(self, diffusion_model, compile_model: bool = False, dtype=torch.float32):
+        super().__init__()
+        self.diffusion_model = diffusion_model
+        self.control_model = None
+        self.dtype = dtype
+
+    def load_control_model(self, control_model):
+        self.control_model = control_model
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, control_scale=1, fbcache_mode="none",
+                partial_info=None, **kwargs):
+        if not x.is_cuda:
+            raise RuntimeError("b200sr.ControlWrapper runs on CUDA (sm_100a) only; there is no CPU fallback")
+        control = None
+        if fbcache_mode != "input_stage2":
+            control = self.control_model(x=c.get("control", None), timesteps=t, xt=x,
+                                         control_vector=c.get("control_vector", None), mask_x=c.get("mask_x", None),
+                                         context=c.get("crossattn", None), y=c.get("vector", None))
+        out = self.diffusion_model(x, timesteps=t, context=c.get("crossattn", None), y=c.get("vector", None),
+                                   control=control, control_scale=control_scale, fbcache_mode=fbcache_mode,
+                                   partial_info=partial_info, **kwargs)
+        if "stage1" in fbcache_mode:
+            return out
+        return out.float()
+
+
+def build_stage2(network_params: Dict, control_params: Dict) -> ControlWrapper:
+    """Convenience: what SR_backbone.__init__ does through instantiate_from_config (SR_model.py:17-51)."""
+    wrapper = ControlWrapper(LightGLVUNet(**network_params))
+    wrapper.load_control_model(GLVControl(**control_params))
+    return wrapper

@@ -92,7 +92,7 @@ def pack_geglu(weight: torch.Tensor, bias: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # dense contractions
 # ------------------------------------------------------------------------------------------------
-def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha) -> Epilogue:
+def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act=0) -> Epilogue:
     e = Epilogue()
     e.bias = _ptr(bias)
     e.rowvec = _ptr(rowvec)
@@ -104,6 +104,7 @@ def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, g
     e.out_fp32 = int(out_fp32)
     e.geglu = int(geglu)
     e.alpha = float(alpha)
+    e.act = int(act)
     return e
 
 
@@ -117,6 +118,7 @@ def gemm(
     rows_per_group: int = 0,
     geglu: bool = False,
     alpha: float = 1.0,
+    act: int = 0,
     out: Optional[torch.Tensor] = None,
     out_fp32: bool = False,
     force_bn: int = 0,
@@ -144,7 +146,7 @@ def gemm(
         r2 = residual if residual.dim() == 2 else residual.reshape(-1, residual.shape[-1])
         assert r2.dtype == bf16 and r2.stride(-1) == 1
         ldr = r2.stride(0)
-    e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha)
+    e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act)
     rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
     check(rc, f"gemm M={M} N={N} K={K}")
     return out
@@ -159,6 +161,7 @@ def conv3x3(
     rowvec: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
     alpha: float = 1.0,
+    act: int = 0,
     out: Optional[torch.Tensor] = None,
     force_bn: int = 0,
 ) -> torch.Tensor:
@@ -174,7 +177,7 @@ def conv3x3(
         out = torch.empty(n, oh, ow, cout, dtype=bf16, device=x.device)
     ldc = out.stride(2)
     ldr = residual.stride(2) if residual is not None else 0
-    e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha)
+    e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha, act)
     rc = _lib.load().b200sr_conv3x3_bf16(
         x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, C.byref(e), force_bn, _stream()
     )
@@ -280,6 +283,17 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     y = torch.empty(n, h, w, c, dtype=bf16, device=x.device)
     check(_lib.load().b200sr_nchw_f32_to_nhwc_bf16(x.data_ptr(), y.data_ptr(), n, c, h * w, float(scale), _stream()),
           "nchw_to_nhwc")
+    return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 of an arbitrary contiguous tensor (conditioning vectors, context tokens)."""
+    if x.dtype == bf16:
+        return x if x.is_contiguous() else x.contiguous()
+    _req(x, torch.float32, "cast_bf16.x")
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    check(_lib.load().b200sr_nchw_f32_to_nhwc_bf16(x.data_ptr(), y.data_ptr(), 1, 1, x.numel(), 1.0, _stream()),
+          "cast_bf16")
     return y
 
 

@@ -107,6 +107,7 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.out_fp32 = e->out_fp32;
   a.geglu = e->geglu;
   a.alpha = e->alpha;
+  a.act = e->act;
   return a;
 }
 

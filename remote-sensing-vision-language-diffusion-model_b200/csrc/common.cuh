@@ -267,6 +267,7 @@ struct EpilogueArgs {
   int out_fp32;
   int geglu;
   float alpha;
+  int act;  // 0 = none, 1 = SiLU (applied last)
 };
 
 }  // namespace b200sr

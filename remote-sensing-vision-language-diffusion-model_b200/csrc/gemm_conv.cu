@@ -56,6 +56,7 @@ struct GemmParams {
   int out_fp32;
   int geglu;
   float alpha;
+  int act;
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -279,6 +280,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            }
             if (p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
@@ -385,6 +390,8 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.out_fp32 = e.out_fp32;
   p.geglu = e.geglu;
   p.alpha = e.alpha;
+  p.act = e.act;
+  if (e.geglu && e.act) return B200SR_EINVAL;
   if (e.out == nullptr) return B200SR_EINVAL;
   if (e.geglu && (e.out_fp32 || e.residual != nullptr || e.rowvec != nullptr || (p.N % 32) != 0)) return B200SR_EINVAL;
   if (p.N % 8 != 0) return B200SR_EINVAL;

@@ -1,0 +1,199 @@
+"""TEST DOUBLE for ``b200sr.ops`` — test infrastructure only, never imported by the package.
+
+Plain torch (CPU-capable) stand-ins with the same signatures, dtypes and layouts as the CUDA
+ops: bf16 storage, fp32 arithmetic inside each op, result rounded to bf16.  Used by the
+``-m "not gpu"`` suite to check the *host wiring* of the drop-in modules (which op is called with
+which tensor, residual/concat order, state_dict keys) against the oracle without a GPU, and as a
+CPU emulation of the bf16 pipeline's rounding.  The product path never routes through this file:
+``b200sr.ops`` has no fallback and raises on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+bf16 = torch.bfloat16
+
+
+def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu=False, alpha=1.0, act=0, out=None,
+         out_fp32=False, force_bn=0):
+    y = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if geglu:
+        n = w.shape[0]
+        y = y.view(y.shape[0], n // 32, 2, 16)
+        y = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(y.shape[0], n // 2)
+    else:
+        y = y * alpha
+        if rowvec is not None:
+            g = torch.arange(y.shape[0]) // rows_per_group if rows_per_group else torch.zeros(y.shape[0], dtype=torch.long)
+            y = y + rowvec[g]
+        if residual is not None:
+            y = y + residual.float().reshape(-1, residual.shape[-1])
+        if act == 1:
+            y = F.silu(y)
+    y = y.reshape(*a.shape[:-1], y.shape[-1])
+    y = y if out_fp32 else y.to(bf16)
+    if out is not None:
+        out.copy_(y.reshape(out.shape))
+        return out
+    return y
+
+
+def conv3x3(x, w, bias=None, *, stride=1, rowvec=None, residual=None, alpha=1.0, act=0, out=None, force_bn=0):
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    w4 = w.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w4, bias, stride=stride, padding=1) * 1.0
+    if alpha != 1.0:
+        y = y * alpha
+    if rowvec is not None:
+        y = y + rowvec[:, :, None, None]
+    y = y.permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    if act == 1:
+        y = F.silu(y)
+    y = y.to(bf16).contiguous()
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def conv3x3_small(x, w, bias, *, addend=None, out_nchw_f32=False):
+    cout, cin = w.shape[0], x.shape[-1]
+    w4 = w.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w4, bias, padding=1)
+    if out_nchw_f32:
+        return y.contiguous()
+    y = y.permute(0, 2, 3, 1)
+    if addend is not None:
+        y = y + addend.float()
+    return y.to(bf16).contiguous()
+
+
+def group_norm(x, weight, bias, *, groups=32, eps=1e-5, silu=False, sft_gamma=None, sft_beta=None, raw=None,
+               control_scale=1.0):
+    shape = x.shape
+    n, c = shape[0], shape[-1]
+    xf = x.float().reshape(n, -1, c).permute(0, 2, 1)
+    y = F.group_norm(xf, groups, weight, bias, eps)
+    if silu:
+        y = F.silu(y)
+    y = y.permute(0, 2, 1).reshape(shape)
+    if sft_gamma is not None:
+        y = y * (1 + sft_gamma.float()) + sft_beta.float()
+        if raw is not None and control_scale != 1.0:
+            y = y * control_scale + raw.float() * (1 - control_scale)
+    return y.to(bf16).contiguous()
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return F.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps).to(bf16)
+
+
+def attention(q, k, v, heads, *, q_col=0, k_col=0, v_col=0, scale=None):
+    b, nq, _ = q.shape
+    c = heads * 64
+    qf = q.float()[..., q_col:q_col + c].reshape(b, nq, heads, 64).transpose(1, 2)
+    kf = k.float()[..., k_col:k_col + c].reshape(b, -1, heads, 64).transpose(1, 2)
+    vf = v.float()[..., v_col:v_col + c].reshape(b, -1, heads, 64).transpose(1, 2)
+    att = torch.softmax(qf @ kf.transpose(-1, -2) * (scale if scale is not None else 0.125), dim=-1)
+    return (att @ vf).transpose(1, 2).reshape(b, nq, c).to(bf16)
+
+
+def nchw_to_nhwc_bf16(x, scale=1.0):
+    return (x * scale).to(bf16).permute(0, 2, 3, 1).contiguous()
+
+
+def nhwc_to_nchw_f32(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def cast_bf16(x):
+    return x.to(bf16).contiguous()
+
+
+def upsample2x(x):
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+
+
+def concat_add(a, b, c=None):
+    if c is not None:
+        b = (b.float() + c.float()).to(bf16)
+    return (torch.cat([a, b], dim=-1) if a is not None else b).contiguous()
+
+
+def axpy(a, b, alpha=1.0):
+    return (a.float() + alpha * b.float()).to(bf16)
+
+
+def silu(x):
+    return F.silu(x.float()).to(bf16)
+
+
+def sinusoid_embedding(t, dim, max_period=10000.0, sin_first=False):
+    t = t.reshape(-1).float()
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None] * freqs[None]
+    parts = [torch.sin(args), torch.cos(args)] if sin_first else [torch.cos(args), torch.sin(args)]
+    return torch.cat(parts, dim=-1).to(bf16)
+
+
+def sampler_pre(x, noise, scalars, cfg_copies=2):
+    sigma, sigma_hat, _, sigma_q, _, s_noise = [float(v) for v in scalars]
+    x_hat = x if noise is None else x + noise * s_noise * max(sigma_hat**2 - sigma**2, 0.0) ** 0.5
+    net = (x_hat / (sigma_q**2 + 1) ** 0.5).to(bf16).permute(0, 2, 3, 1)
+    return x_hat, torch.cat([net] * cfg_copies, 0).contiguous()
+
+
+def sampler_post(eps, x_hat, scalars, use_cfg=True, want_denoised=True):
+    _, sigma_hat, sigma_next, sigma_q, cfg, _ = [float(v) for v in scalars]
+    if use_cfg:
+        eu, ec = eps.chunk(2)
+        du, dc = eu * -sigma_q + x_hat, ec * -sigma_q + x_hat
+        den = du + cfg * (dc - du)
+    else:
+        den = eps * -sigma_q + x_hat
+    return x_hat + (x_hat - den) / sigma_hat * (sigma_next - sigma_hat), den
+
+
+def euler_from_denoised(denoised, x_hat, scalars):
+    _, sigma_hat, sigma_next = [float(v) for v in scalars[:3]]
+    return x_hat + (x_hat - denoised) / sigma_hat * (sigma_next - sigma_hat)
+
+
+def tile_accumulate(tile, weight, acc, cnt, h0, w0):
+    th, tw = tile.shape[-2:]
+    acc[:, :, h0:h0 + th, w0:w0 + tw] += tile * weight
+    cnt[:, :, h0:h0 + th, w0:w0 + tw] += weight
+
+
+def tile_normalize(acc, cnt):
+    return acc / cnt
+
+
+def rel_l1_similarity(prev, cur, threshold):
+    d = ((prev.float() - cur.float()).abs().mean() / (prev.float().abs().mean() + 1e-6))
+    return torch.stack([d, (d < threshold[0]).float()])
+
+
+def sr3_update(x, eps, noise, scalars):
+    cr, crm1, c1, c2, lv = [float(v) for v in scalars]
+    x0 = (cr * x - crm1 * eps).clamp(-1, 1)
+    out = c1 * x0 + c2 * x
+    return out if noise is None else out + noise * math.exp(0.5 * lv)
+
+
+ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("F", "torch", "math")]
+
+
+def install(monkeypatch, ops_module):
+    for name in ALL:
+        if hasattr(ops_module, name):
+            monkeypatch.setattr(ops_module, name, globals()[name])
