@@ -99,6 +99,10 @@ def load() -> C.CDLL:
     return lib
 
 
-def check(rc: int, what: str) -> None:
+LAUNCHES = [0]  # number of b200sr kernels enqueued so far (each C-ABI call reports its kernel count here)
+
+
+def check(rc: int, what: str, kernels: int = 1) -> None:
+    LAUNCHES[0] += kernels
     if rc != 0:
         raise B200SRError(f"{what} failed: {_ERRORS.get(rc, rc)}")

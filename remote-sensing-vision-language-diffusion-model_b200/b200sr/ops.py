@@ -23,6 +23,40 @@ from ._lib import Epilogue, check
 bf16 = torch.bfloat16
 
 
+def launch_count() -> int:
+    """Number of b200sr kernels enqueued by this process so far."""
+    return _lib.LAUNCHES[0]
+
+
+# Optional per-launch timing of the dense kernels (bench.py roofline leg): when a list is installed,
+# every gemm / conv3x3 / attention launch is bracketed by CUDA events on the launching stream and
+# appended as (kind, algorithmic_flops, start_event, end_event).
+_profile = None
+
+
+def set_profile(records) -> None:
+    global _profile
+    _profile = records
+
+
+class _Timed:
+    def __init__(self, kind: str, flops: float):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if _profile is not None:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None:
+            self.t1.record()
+            _profile.append((self.kind, self.flops, self.t0, self.t1))
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -147,7 +181,8 @@ def gemm(
         assert r2.dtype == bf16 and r2.stride(-1) == 1
         ldr = r2.stride(0)
     e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act)
-    rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
+    with _Timed("gemm", 2.0 * M * N * K):
+        rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
     check(rc, f"gemm M={M} N={N} K={K}")
     return out
 
@@ -178,9 +213,10 @@ def conv3x3(
     ldc = out.stride(2)
     ldr = residual.stride(2) if residual is not None else 0
     e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha, act)
-    rc = _lib.load().b200sr_conv3x3_bf16(
-        x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, C.byref(e), force_bn, _stream()
-    )
+    with _Timed("conv3x3", 2.0 * n * oh * ow * cout * 9 * cin):
+        rc = _lib.load().b200sr_conv3x3_bf16(
+            x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, C.byref(e), force_bn, _stream()
+        )
     check(rc, f"conv3x3 N={n} H={h} W={wd} Cin={cin} Cout={cout} s={stride}")
     return out
 
@@ -236,7 +272,7 @@ def group_norm(
         x.data_ptr(), y.data_ptr(), _ptr(weight), _ptr(bias), n, hw, c, groups, eps, int(silu), _ptr(sft_gamma),
         _ptr(sft_beta), _ptr(raw), float(control_scale), ws.data_ptr(), _stream()
     )
-    check(rc, f"group_norm N={n} HW={hw} C={c}")
+    check(rc, f"group_norm N={n} HW={hw} C={c}", kernels=2)
     return y
 
 
@@ -265,10 +301,11 @@ def attention(
     b, nq, ldq = q.shape
     nk = k.shape[1]
     out = torch.empty(b, nq, heads * 64, dtype=bf16, device=q.device)
-    rc = _lib.load().b200sr_attention_d64(
-        q.data_ptr(), ldq, q_col, k.data_ptr(), k.shape[2], k_col, v.data_ptr(), v.shape[2], v_col, out.data_ptr(),
-        heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _stream()
-    )
+    with _Timed("attention", 4.0 * b * heads * nq * nk * 64):
+        rc = _lib.load().b200sr_attention_d64(
+            q.data_ptr(), ldq, q_col, k.data_ptr(), k.shape[2], k_col, v.data_ptr(), v.shape[2], v_col, out.data_ptr(),
+            heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _stream()
+        )
     check(rc, f"attention B={b} H={heads} Nq={nq} Nk={nk}")
     return out
 
@@ -412,7 +449,7 @@ def rel_l1_similarity(prev: torch.Tensor, cur: torch.Tensor, threshold: torch.Te
         _rel_ws[key] = ws
     res = torch.empty(2, dtype=torch.float32, device=prev.device)
     check(_lib.load().b200sr_rel_l1_similarity(prev.data_ptr(), cur.data_ptr(), prev.numel(), threshold.data_ptr(),
-                                               ws.data_ptr(), res.data_ptr(), _stream()), "rel_l1_similarity")
+                                               ws.data_ptr(), res.data_ptr(), _stream()), "rel_l1_similarity", kernels=2)
     return res
 
 

@@ -1,0 +1,291 @@
+"""Stage-2 sampler stack, B200-native: sigma tables, the discrete eps denoiser, linear CFG and the
+RestoreEDMSampler step, restated on top of the fused sampler kernels, plus a CUDA-graphed step
+engine.
+
+Mirrored reference code (relative to the reference root):
+  LegacyDDPMDiscretization                   sgm/modules/diffusionmodules/discretizer.py:42-69
+  DiscreteDenoiserWithControl + EpsScaling   denoiser.py:31-78, denoiser_scaling.py:16-22
+  LinearCFG                                  guiders.py:44-74
+  RestoreEDMSampler.{init_loop,step,sampler_step,denoise}   sampling.py:527-694
+  first-block cache                          models/modules/DFBCache.py:59-134
+  TiledRestoreEDMSampler, gaussian_weights, _sliding_windows   sampling.py:697-757, :830-863
+  loop body of SR_backbone.just_sampling     models/SR_model.py:242-291
+
+All per-step scalars (sigma, sigma_hat, quantised sigma / index, CFG scale) are known before the
+loop starts, so they are computed once on the host with the reference's own fp32 arithmetic and
+shipped to the device as a 6-float vector per step: no `.item()` round trips inside the step
+except the single cache-decision flag the reference also reads.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+SIGMA_MAX = 14.6146
+
+
+# ------------------------------------------------------------------------------------------------
+# schedule (host side)
+# ------------------------------------------------------------------------------------------------
+def legacy_ddpm_sigmas(n: int, do_append_zero: bool = True, flip: bool = False, num_timesteps: int = 1000,
+                       linear_start: float = 0.00085, linear_end: float = 0.0120) -> torch.Tensor:
+    """discretizer.py:18-23, :42-69 (+ make_beta_schedule util.py:19-32).  CPU fp32 tensor."""
+    betas = torch.linspace(linear_start**0.5, linear_end**0.5, num_timesteps, dtype=torch.float64) ** 2
+    alphas_cumprod = np.cumprod(1.0 - betas.numpy(), axis=0)
+    if n < num_timesteps:
+        ts = np.linspace(num_timesteps - 1, 0, n, endpoint=False).astype(int)[::-1]
+        alphas_cumprod = alphas_cumprod[ts]
+    elif n != num_timesteps:
+        raise ValueError
+    sig = torch.tensor((1 - alphas_cumprod) / alphas_cumprod, dtype=torch.float32) ** 0.5
+    sig = torch.flip(sig, (0,))
+    if do_append_zero:
+        sig = torch.cat([sig, sig.new_zeros([1])])
+    return torch.flip(sig, (0,)) if flip else sig
+
+
+class StepSchedule:
+    """Everything the reference derives per step from (sigmas, s_churn, s_noise, guider), on the host."""
+
+    def __init__(self, num_steps=50, s_churn=5.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.003, cfg_scale=4.0,
+                 cfg_scale_min=7.5):
+        self.sigmas = legacy_ddpm_sigmas(num_steps)                                   # [num_steps + 1], descending
+        self.table = legacy_ddpm_sigmas(1000, do_append_zero=False, flip=True)        # denoiser.sigmas (ascending)
+        self.num_steps = num_steps
+        rows, idxs = [], []
+        for i in range(num_steps):
+            sigma = self.sigmas[i]
+            gamma = min(s_churn / num_steps, 2**0.5 - 1) if s_tmin <= float(sigma) <= s_tmax else 0.0
+            sigma_hat = sigma * (gamma + 1.0)                                          # sampling.py:600
+            idx = int((sigma_hat - self.table).abs().argmin())                         # denoiser.py:49-51
+            sigma_q = self.table[idx]
+            cfg = (cfg_scale - cfg_scale_min) * sigma_hat / SIGMA_MAX + cfg_scale_min  # guiders.py:48
+            rows.append([float(sigma), float(sigma_hat), float(self.sigmas[i + 1]), float(sigma_q), float(cfg),
+                         float(s_noise) if gamma > 0 else 0.0])
+            idxs.append(idx)
+        self.scalars = torch.tensor(rows, dtype=torch.float32)   # [steps, 6]
+        self.idx = torch.tensor(idxs, dtype=torch.float32)       # sigma index fed to the timestep embedding
+        self.init_scale = float(torch.sqrt(1.0 + self.sigmas[0] ** 2.0))               # sampling.py:50
+
+
+# ------------------------------------------------------------------------------------------------
+# tiles (host side)
+# ------------------------------------------------------------------------------------------------
+def sliding_windows(h: int, w: int, tile_size: int, tile_stride: int) -> List[Tuple[int, int, int, int]]:
+    """sampling.py:850-863."""
+    his = list(range(0, h - tile_size + 1, tile_stride))
+    if (h - tile_size) % tile_stride != 0:
+        his.append(h - tile_size)
+    wis = list(range(0, w - tile_size + 1, tile_stride))
+    if (w - tile_size) % tile_stride != 0:
+        wis.append(w - tile_size)
+    return [(hi, hi + tile_size, wi, wi + tile_size) for hi in his for wi in wis]
+
+
+def gaussian_weights(tile_width: int, tile_height: int) -> torch.Tensor:
+    """sampling.py:830-847 (var 0.01, the x midpoint uses (w-1)/2, the y midpoint h/2). CPU fp32 [h, w]."""
+    var = 0.01
+    mid = (tile_width - 1) / 2
+    xs = [math.exp(-(x - mid) * (x - mid) / (tile_width * tile_width) / (2 * var)) / math.sqrt(2 * math.pi * var)
+          for x in range(tile_width)]
+    mid = tile_height / 2
+    ys = [math.exp(-(y - mid) * (y - mid) / (tile_height * tile_height) / (2 * var)) / math.sqrt(2 * math.pi * var)
+          for y in range(tile_height)]
+    return torch.tensor(np.outer(ys, xs), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# the step engine
+# ------------------------------------------------------------------------------------------------
+class Stage2Engine:
+    """Runs RestoreEDMSampler steps for one latent (batch B, CFG doubles it) on one GPU.
+
+    ``wrapper`` is a ``b200sr.modules.ControlWrapper``.  One step =
+        sampler_pre kernel -> control net + UNet (all C-ABI kernels) -> sampler_post kernel
+    optionally captured into CUDA graphs (one for the uncached step, two for the first-block-cache
+    protocol: "input stage + similarity" and "output stage + update").
+    """
+
+    def __init__(self, wrapper, num_steps=50, s_churn=5.0, s_noise=1.003, cfg_scale=4.0, cfg_scale_min=7.5,
+                 control_scale=1.0, use_graphs=True, device="cuda"):
+        self.wrapper = wrapper
+        self.sched = StepSchedule(num_steps, s_churn, 0.0, float("inf"), s_noise, cfg_scale, cfg_scale_min)
+        self.control_scale = control_scale
+        self.use_graphs = use_graphs
+        self.device = torch.device(device)
+        self._scalars_dev = self.sched.scalars.to(self.device)   # [steps, 6]
+        self._idx_dev = self.sched.idx.to(self.device)
+        self.cond = None
+        self._graphs: Dict[str, object] = {}
+        self._static: Dict[str, torch.Tensor] = {}
+        self.trace: List[Tuple[str, float]] = []
+        self._prev_h = None
+        self._final_decode = None
+        self.launches: Dict[str, int] = {}   # b200sr kernels launched by one run of each step body
+
+    # -- conditioning ---------------------------------------------------------------------------
+    def set_condition(self, c: Dict[str, torch.Tensor], uc: Dict[str, torch.Tensor]) -> None:
+        """guiders.py:65-74: batch = [uncond ; cond]; casts once to bf16 (context / vector / control)."""
+        cat = lambda k: torch.cat((uc[k], c[k]), 0).to(self.device).float().contiguous()  # noqa: E731
+        new = {"crossattn": ops.cast_bf16(cat("crossattn")), "vector": ops.cast_bf16(cat("vector")),
+               "control": ops.nchw_to_nhwc_bf16(cat("control")).permute(0, 3, 1, 2)}
+        if self.cond is not None and all(self.cond[k].shape == new[k].shape for k in new):
+            for k in new:  # keep addresses stable for captured graphs
+                self.cond[k].copy_(new[k])
+        else:
+            self.cond = new
+            self._graphs.clear()
+        self.reset_cache()
+
+    def reset_cache(self):
+        self._prev_valid = False
+        self._final_valid = False
+        self.trace = []
+
+    def init_latent(self, z: torch.Tensor) -> torch.Tensor:
+        return z.to(self.device).float() * self.sched.init_scale
+
+    # -- building blocks ------------------------------------------------------------------------
+    def _buffers(self, x: torch.Tensor):
+        st = self._static
+        if "x" not in st or st["x"].shape != x.shape:
+            st.clear()
+            self._graphs.clear()
+            b = x.shape[0]
+            st["x"] = torch.empty_like(x)
+            st["noise"] = torch.zeros_like(x)
+            st["sc"] = torch.empty(6, dtype=torch.float32, device=self.device)
+            st["t"] = torch.empty(2 * b, dtype=torch.float32, device=self.device)
+            st["thr"] = torch.empty(1, dtype=torch.float32, device=self.device)
+        return st
+
+    def _load_step(self, x, i, noise):
+        st = self._buffers(x)
+        st["x"].copy_(x, non_blocking=True)
+        if noise is not None:
+            st["noise"].copy_(noise, non_blocking=True)
+        st["sc"].copy_(self._scalars_dev[i], non_blocking=True)
+        st["t"].fill_(0).add_(self._idx_dev[i])
+        return st
+
+    def _body_full(self):
+        st = self._static
+        x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
+        eps = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "none", None)
+        x_next, den = ops.sampler_post(eps, x_hat, st["sc"], True, True)
+        st["x_next"], st["den"] = x_next, den
+
+    def _body_stage1(self):
+        st = self._static
+        x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
+        info = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "input_stage1", None)
+        st["x_hat"], st["info"] = x_hat, info
+        h = info["h"].permute(0, 2, 3, 1)
+        if "prev_h" not in st:
+            st["prev_h"] = torch.zeros_like(h)
+            st["final"] = torch.zeros_like(st["x"])
+        st["sim"] = ops.rel_l1_similarity(st["prev_h"], h, st["thr"])
+
+    def _body_stage2(self):
+        st = self._static
+        info = st["info"]
+        st["prev_h"].copy_(info["h"].permute(0, 2, 3, 1))                 # context.prev = h.clone()  (sampling.py:580)
+        eps = self.wrapper(st["x_hat"], st["t"], self.cond, self.control_scale, "input_stage2", info)
+        x_next, den = ops.sampler_post(eps, st["x_hat"], st["sc"], True, True)
+        st["final"].copy_(den)                                           # context.final_decode = denoised.clone()
+        st["x_next"] = x_next
+
+    def _body_hit(self):
+        st = self._static
+        st["x_next_hit"] = ops.euler_from_denoised(st["final"], st["x_hat"], st["sc"])
+
+    def _run(self, name: str, body):
+        if not self.use_graphs:
+            n0 = ops.launch_count()
+            body()
+            self.launches[name] = ops.launch_count() - n0
+            return
+        g = self._graphs.get(name)
+        if g is None:
+            # eager warm-up (packs weights, sizes workspaces), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                body()
+            self.launches[name] = ops.launch_count() - n0   # kernels recorded in (and replayed by) this graph
+            self._graphs[name] = g
+        g.replay()
+
+    # -- public API -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, x: torch.Tensor, i: int, noise: Optional[torch.Tensor] = None, threshold: float = 0.0):
+        """One RestoreEDMSampler.step (sampling.py:659-694).  Returns (x_next, new_threshold).
+        `noise` replaces torch.randn_like(x) (sampling.py:605); required when s_churn > 0."""
+        if self.cond is None:
+            raise RuntimeError("call set_condition(c, uc) first")
+        if noise is None and float(self.sched.scalars[i, 5]) > 0:
+            noise = torch.randn_like(x)
+        self._load_step(x, i, noise)
+        st = self._static
+        if threshold <= 0:                                   # sampling.py:549-555
+            self._run("full", self._body_full)
+            return st["x_next"].clone(), threshold
+        st["thr"].fill_(float(threshold))
+        self._run("stage1", self._body_stage1)
+        diff, flag = st["sim"].tolist()                      # the one host sync per step (DFBCache.py:112)
+        use_cache = self._prev_valid and flag > 0.5
+        cache_th = diff if self._prev_valid else threshold   # DFBCache.py:122-134
+        if use_cache and self._final_valid:                  # sampling.py:573-576
+            self._run("hit", self._body_hit)
+            self.trace.append(("hit", cache_th))
+            return st["x_next_hit"].clone(), threshold
+        self._run("stage2", self._body_stage2)
+        self._prev_valid = self._final_valid = True
+        self.trace.append(("miss", cache_th))
+        return st["x_next"].clone(), cache_th
+
+    @torch.no_grad()
+    def sample(self, z: torch.Tensor, noises: Optional[List[torch.Tensor]] = None, threshold: float = 0.0,
+               dec: float = 1.0) -> torch.Tensor:
+        """The 50-step loop of SR_backbone.just_sampling (SR_model.py:265-291) for an already encoded latent."""
+        x = self.init_latent(z)
+        self.reset_cache()
+        thr = threshold
+        for i in range(self.sched.num_steps):
+            x, thr = self.step(x, i, None if noises is None else noises[i], thr)
+            thr *= dec
+        return x
+
+    @torch.no_grad()
+    def tiled_step(self, x: torch.Tensor, i: int, noise: torch.Tensor, lq: torch.Tensor, c, uc, tile: int = 128,
+                   stride: int = 96, windows=None) -> torch.Tensor:
+        """One step of the tiled sampler (sampling.py:716-756) over `windows` (default: all):
+        per tile the threshold<=0 path, the full-latent noise sliced per tile, control sliced per tile.
+        Returns (acc, cnt) contributions when `windows` is a subset, else the blended latent."""
+        all_w = sliding_windows(x.shape[2], x.shape[3], tile, stride)
+        mine = all_w if windows is None else windows
+        wgt = getattr(self, "_tile_w", None)
+        if wgt is None or wgt.shape[-1] != tile:
+            wgt = gaussian_weights(tile, tile).to(self.device)
+            self._tile_w = wgt
+        acc, cnt = torch.zeros_like(x), torch.zeros_like(x)
+        for (h0, h1, w0, w1) in mine:
+            ct = dict(c, control=lq[:, :, h0:h1, w0:w1].contiguous())
+            uct = dict(uc, control=lq[:, :, h0:h1, w0:w1].contiguous())
+            self.set_condition(ct, uct)
+            xt, _ = self.step(x[:, :, h0:h1, w0:w1].contiguous(), i, noise[:, :, h0:h1, w0:w1].contiguous(), 0.0)
+            ops.tile_accumulate(xt, wgt, acc, cnt, h0, w0)
+        if windows is not None:
+            return acc, cnt
+        return ops.tile_normalize(acc, cnt)

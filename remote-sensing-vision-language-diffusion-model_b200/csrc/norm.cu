@@ -21,7 +21,7 @@ namespace b200sr {
 __global__ void __launch_bounds__(1024)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
                 int pix_per_cta, int chunks) {
-  extern __shared__ float s_red[];  // [C] sums, [C] sumsq
+  extern __shared__ float s_red[];  // [P][C] sums, then [P][C] sums of squares (no atomics: deterministic)
   const int C8 = C >> 3;
   const int P = blockDim.x / C8;
   const int cv = threadIdx.x % C8;
@@ -30,9 +30,8 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   const int chunk = blockIdx.x;
   const int p_begin = chunk * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
-
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
-  __syncthreads();
+  float* s_sum = s_red;
+  float* s_sq = s_red + P * C;
 
   float s[8], q[8];
 #pragma unroll
@@ -72,17 +71,19 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_red[cv * 8 + j], s[j]);
-      atomicAdd(&s_red[C + cv * 8 + j], q[j]);
+      s_sum[pl * C + cv * 8 + j] = s[j];
+      s_sq[pl * C + cv * 8 + j] = q[j];
     }
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += s_red[c];
-      b += s_red[C + c];
+    for (int pp = 0; pp < P; ++pp) {
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += s_sum[pp * C + c];
+        b += s_sq[pp * C + c];
+      }
     }
     float* dst = partial + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
     dst[0] = a;
@@ -231,7 +232,7 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   int threads, P, ppc, chunks;
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
   dim3 grid(chunks, N);
-  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  gn_stats_kernel<<<grid, threads, 2 * static_cast<size_t>(P) * C * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                                     workspace, HW, C, groups, ppc, chunks);
   GnApplyArgs a;
   a.x = reinterpret_cast<const __nv_bfloat16*>(x);
