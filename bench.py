@@ -205,7 +205,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     ops.set_profile(None)
     torch.cuda.synchronize()
     agg = {}
-    for kind, fl, a, b in recs:
+    for kind, fl, a, b, _desc in recs:
         d = agg.setdefault(kind, [0.0, 0.0, 0])
         d[0] += fl
         d[1] += a.elapsed_time(b)

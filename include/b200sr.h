@@ -110,6 +110,10 @@ int b200sr_concat_add(const void* a, int32_t Ca, const void* b, int32_t Cb, cons
 /* y = a + alpha * b, bf16. */
 int b200sr_axpy_bf16(const void* a, const void* b, void* y, float alpha, int64_t n, void* stream);
 
+/* y[rows, Cpad] = [x[rows, C] | zeros], bf16: pads the 4-channel latent to a 64-channel K chunk so the stem
+ * convolutions (openaimodel.py:695-701, SR_modules.py:478-480) use b200sr_conv3x3_bf16. */
+int b200sr_pad_channels(const void* x, void* y, int32_t C, int32_t Cpad, int64_t rows, void* stream);
+
 /* y = silu(x), bf16 (embedding path: openaimodel.py:281-283, :660-662). */
 int b200sr_silu_bf16(const void* x, void* y, int64_t n, void* stream);
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200sr_concat_add": (c_int, [P, c_int, P, c_int, P, P, c_i64, P]),
     "b200sr_axpy_bf16": (c_int, [P, P, P, c_float, c_i64, P]),
     "b200sr_silu_bf16": (c_int, [P, P, c_i64, P]),
+    "b200sr_pad_channels": (c_int, [P, P, c_int, c_int, c_i64, P]),
     "b200sr_sinusoid_embedding": (c_int, [P, P, c_int, c_int, c_float, c_int, P]),
     "b200sr_sampler_pre": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "b200sr_sampler_post": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
@@ -102,7 +103,12 @@ def load() -> C.CDLL:
 LAUNCHES = [0]  # number of b200sr kernels enqueued so far (each C-ABI call reports its kernel count here)
 
 
+TRACE = None  # optional list: one entry per kernel enqueued ("what" of the C-ABI call), for joining with ncu launch lists
+
+
 def check(rc: int, what: str, kernels: int = 1) -> None:
     LAUNCHES[0] += kernels
+    if TRACE is not None:
+        TRACE.extend([what] * kernels)
     if rc != 0:
         raise B200SRError(f"{what} failed: {_ERRORS.get(rc, rc)}")

@@ -264,9 +264,29 @@ class CrossAttention(nn.Module, Packed):
             qkv = ops.gemm(x, w)
             return ops.attention(qkv, qkv, qkv, self.heads, q_col=0, k_col=inner, v_col=2 * inner, scale=self.scale)
         q = _linear(self, "q", self.to_q, x)
-        wkv = self._pk("kv", (self.to_k.weight, self.to_v.weight), lambda k, v: torch.cat([k, v], 0).to(bf16).contiguous())
-        kv = ops.gemm(context, wkv)
+        if context is self.__dict__.get("_static_ctx"):
+            kv = self._static_kv  # hoisted by bind_static_context(): the text context is constant over the steps
+        else:
+            kv = ops.gemm(context, self._wkv())
         return ops.attention(q, kv, kv, self.heads, q_col=0, k_col=0, v_col=inner, scale=self.scale)
+
+    def _wkv(self):
+        return self._pk("kv", (self.to_k.weight, self.to_v.weight), lambda k, v: torch.cat([k, v], 0).to(bf16).contiguous())
+
+    def bind_static_context(self, context: Optional[torch.Tensor]) -> None:
+        """Precompute K/V of a context that stays constant across sampler steps (the text embedding:
+        SURVEY.md 8(a) a8 notes the reference re-projects it every step).  `context` must be the very
+        tensor object later passed to forward(); results are written in place when the buffer exists
+        so captured CUDA graphs stay valid.  Pass None to unbind."""
+        if context is None:
+            self.__dict__.pop("_static_ctx", None)
+            self.__dict__.pop("_static_kv", None)
+            return
+        old = self.__dict__.get("_static_kv")
+        shape = (*context.shape[:-1], 2 * self.to_q.weight.shape[0])
+        out = old if (old is not None and tuple(old.shape) == shape and old.device == context.device) else None
+        self._static_kv = ops.gemm(context, self._wkv(), out=out)
+        self._static_ctx = context
 
     def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
                 residual: Optional[torch.Tensor] = None, alpha: float = 1.0):
@@ -370,13 +390,15 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
 
 
 def _stem_conv(conv: nn.Conv2d, x_nhwc: torch.Tensor, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """latent (<= 8 channels) -> features: direct convolution kernel (input_blocks.0.0, input_hint_block.0)."""
+    """latent (<= 8 channels) -> features (input_blocks.0.0, input_hint_block.0): the input is zero-padded to
+    one 64-channel K chunk so the convolution runs on the tcgen05 implicit-GEMM path (the direct
+    few-channel kernel is 60x slower at 128^2)."""
     cache = conv.__dict__.setdefault("_pk_cache", {})
     key = (conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)
     if cache.get("key") != key:
         with torch.no_grad():
-            cache["key"], cache["w"], cache["b"] = key, ops.pack_conv3x3(conv.weight), _F32(conv.bias)
-    return ops.conv3x3_small(x_nhwc, cache["w"], cache["b"], addend=addend)
+            cache["key"], cache["w"], cache["b"] = key, ops.pack_conv3x3_padded(conv.weight, 64), _F32(conv.bias)
+    return ops.conv3x3(ops.pad_channels(x_nhwc, 64), cache["w"], cache["b"], residual=addend)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -739,6 +761,16 @@ class ControlWrapper(nn.Module):
         if "stage1" in fbcache_mode:
             return out
         return out.float()
+
+
+def bind_text_context(wrapper: nn.Module, context: Optional[torch.Tensor]) -> int:
+    """Hoist the text K/V projections of every cross-attention (attn2) out of the step loop."""
+    n = 0
+    for m in wrapper.modules():
+        if isinstance(m, BasicTransformerBlock) and not m.disable_self_attn:
+            m.attn2.bind_static_context(context)
+            n += 1
+    return n
 
 
 def build_stage2(network_params: Dict, control_params: Dict) -> ControlWrapper:

@@ -40,8 +40,8 @@ def set_profile(records) -> None:
 
 
 class _Timed:
-    def __init__(self, kind: str, flops: float):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind: str, flops: float, desc: str = ""):
+        self.kind, self.flops, self.desc = kind, flops, desc
 
     def __enter__(self):
         if _profile is not None:
@@ -53,7 +53,7 @@ class _Timed:
     def __exit__(self, *exc):
         if _profile is not None:
             self.t1.record()
-            _profile.append((self.kind, self.flops, self.t0, self.t1))
+            _profile.append((self.kind, self.flops, self.t0, self.t1, self.desc))
         return False
 
 
@@ -181,7 +181,7 @@ def gemm(
         assert r2.dtype == bf16 and r2.stride(-1) == 1
         ldr = r2.stride(0)
     e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act)
-    with _Timed("gemm", 2.0 * M * N * K):
+    with _Timed("gemm", 2.0 * M * N * K, f"M{M} N{N} K{K}{' geglu' if geglu else ''}"):
         rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
     check(rc, f"gemm M={M} N={N} K={K}")
     return out
@@ -213,7 +213,7 @@ def conv3x3(
     ldc = out.stride(2)
     ldr = residual.stride(2) if residual is not None else 0
     e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha, act)
-    with _Timed("conv3x3", 2.0 * n * oh * ow * cout * 9 * cin):
+    with _Timed("conv3x3", 2.0 * n * oh * ow * cout * 9 * cin, f"{n}x{h}x{wd} Cin{cin} Cout{cout} s{stride}"):
         rc = _lib.load().b200sr_conv3x3_bf16(
             x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, C.byref(e), force_bn, _stream()
         )
@@ -301,7 +301,7 @@ def attention(
     b, nq, ldq = q.shape
     nk = k.shape[1]
     out = torch.empty(b, nq, heads * 64, dtype=bf16, device=q.device)
-    with _Timed("attention", 4.0 * b * heads * nq * nk * 64):
+    with _Timed("attention", 4.0 * b * heads * nq * nk * 64, f"B{b} H{heads} Nq{nq} Nk{nk}"):
         rc = _lib.load().b200sr_attention_d64(
             q.data_ptr(), ldq, q_col, k.data_ptr(), k.shape[2], k_col, v.data_ptr(), v.shape[2], v_col, out.data_ptr(),
             heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _stream()
@@ -369,6 +369,23 @@ def axpy(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
     check(_lib.load().b200sr_axpy_bf16(a.data_ptr(), b.data_ptr(), y.data_ptr(), float(alpha), a.numel(), _stream()),
           "axpy")
     return y
+
+
+def pad_channels(x: torch.Tensor, cpad: int) -> torch.Tensor:
+    """[..., C] bf16 -> [..., cpad] bf16 with zero fill."""
+    _req(x, bf16, "pad_channels.x")
+    c = x.shape[-1]
+    y = torch.empty(*x.shape[:-1], cpad, dtype=bf16, device=x.device)
+    check(_lib.load().b200sr_pad_channels(x.data_ptr(), y.data_ptr(), c, cpad, x.numel() // c, _stream()), "pad_channels")
+    return y
+
+
+def pack_conv3x3_padded(weight: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> bf16 [Cout, 9*cin_pad] (zero weights for the padded input channels)."""
+    co, ci, kh, kw = weight.shape
+    w = torch.zeros(co, 3, 3, cin_pad, dtype=weight.dtype, device=weight.device)
+    w[..., :ci] = weight.detach().permute(0, 2, 3, 1)
+    return w.reshape(co, 9 * cin_pad).to(bf16).contiguous()
 
 
 def silu(x: torch.Tensor) -> torch.Tensor:

@@ -112,8 +112,9 @@ class Stage2Engine:
     """
 
     def __init__(self, wrapper, num_steps=50, s_churn=5.0, s_noise=1.003, cfg_scale=4.0, cfg_scale_min=7.5,
-                 control_scale=1.0, use_graphs=True, device="cuda"):
+                 control_scale=1.0, use_graphs=True, device="cuda", hoist_text_kv=True):
         self.wrapper = wrapper
+        self.hoist_text_kv = hoist_text_kv
         self.sched = StepSchedule(num_steps, s_churn, 0.0, float("inf"), s_noise, cfg_scale, cfg_scale_min)
         self.control_scale = control_scale
         self.use_graphs = use_graphs
@@ -140,6 +141,10 @@ class Stage2Engine:
         else:
             self.cond = new
             self._graphs.clear()
+        if self.hoist_text_kv and hasattr(self.wrapper, "modules"):
+            from .modules import bind_text_context
+
+            bind_text_context(self.wrapper, self.cond["crossattn"])
         self.reset_cache()
 
     def reset_cache(self):

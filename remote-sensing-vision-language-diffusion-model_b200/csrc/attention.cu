@@ -23,7 +23,7 @@ namespace b200sr {
 static constexpr int ATT_BM = 128;   // query rows per CTA
 static constexpr int ATT_BN = 128;   // keys per block
 static constexpr int ATT_D = 64;     // head dim
-static constexpr int ATT_THREADS = 192;
+static constexpr int ATT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
 static constexpr int ATT_STAGES = 2;
 static constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KiB
 static constexpr int ATT_TMEM_COLS = 256;
@@ -51,6 +51,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -66,6 +72,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* p_full = s_full + 1;
   uint64_t* o_done = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  float* s_xch = reinterpret_cast<float*>(tmem_slot + 2);  // [2][2][128] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BM;
@@ -82,7 +89,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);  // one arrive per softmax warp
+    mbar_init(p_full, 8);  // one arrive per softmax warp
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -166,33 +173,40 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else {
     // ================================ softmax / correction / epilogue ================================
+    // Two threads per query row: warp w owns TMEM lane quadrant (w & 3) and key columns
+    // [64*half, 64*half + 64) of every S block, half = (w - 2) >> 2.  The row maximum is exchanged
+    // through shared memory once per block; row sums stay per-thread until the epilogue.
     const int sub = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = sub * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
     float m_used = -INFINITY;  // maximum the exponentials are currently taken against (log2 units)
-    float l = 0.f;             // running sum of exponentials
+    float l = 0.f;             // this thread's share of the running sum of exponentials
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float s[128];
+      float s[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t a[32];
-        tmem_ld32(tmem + lane_base + ATT_COL_S + c * 32, a);
+        tmem_ld32(tmem + lane_base + ATT_COL_S + half * 64 + c * 32, a);
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(a[i]);
       }
       tmem_ld_wait();
-      const int kv_left = p.Nk - j * ATT_BN;
-      if (kv_left < ATT_BN) {
+      const int kv_left = p.Nk - j * ATT_BN - half * 64;
+      if (kv_left < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < 64; ++i)
           if (i >= kv_left) s[i] = -INFINITY;
       }
       float mx = s[0];
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
-      mx *= p.scale_log2;
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      float* xch = s_xch + (j & 1) * 256;
+      xch[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]) * p.scale_log2;
       // lazy rescale: only when the maximum grew by more than 8 (factor 256) since the last one
       const bool grow = mx > m_used + 8.0f;
       if (j == 0) {
@@ -200,60 +214,56 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       } else if (__any_sync(0xffffffffu, grow)) {
         float alpha = 1.0f;
         if (grow) {
-          alpha = exp2f(m_used - mx);
+          alpha = ex2_approx(m_used - mx);
           m_used = mx;
           l *= alpha;
         }
+        uint32_t o[32];
+        tmem_ld32(tmem + lane_base + ATT_COL_O + half * 32, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem + lane_base + ATT_COL_O + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem + lane_base + ATT_COL_O + c * 32, o);
-        }
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tmem + lane_base + ATT_COL_O + half * 32, o);
       }
-      float sum = 0.f;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e0 = exp2f(fmaf(s[c * 64 + 2 * i], p.scale_log2, -m_used));
-          const float e1 = exp2f(fmaf(s[c * 64 + 2 * i + 1], p.scale_log2, -m_used));
-          sum += e0 + e1;
-          pk[i] = pack_bf16x2(e0, e1);
-        }
-        tmem_st32(tmem + lane_base + ATT_COL_P + c * 32, pk);
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = ex2_approx(fmaf(s[2 * i], p.scale_log2, -m_used));
+        const float e1 = ex2_approx(fmaf(s[2 * i + 1], p.scale_log2, -m_used));
+        sum0 += e0;
+        sum1 += e1;
+        pk[i] = pack_bf16x2(e0, e1);
       }
-      l += sum;
+      tmem_st32(tmem + lane_base + ATT_COL_P + half * 32, pk);
+      l += sum0 + sum1;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l -> bf16 -> global
+    // epilogue: O / l -> bf16 -> global; each thread writes 32 of the 64 output columns of its row
+    float* xch = s_xch + (nblk & 1) * 256;
+    xch[half * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[(half ^ 1) * 128 + r];
     mbar_wait(o_done, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int q = q0 + r;
+    uint32_t o[32];
+    tmem_ld32(tmem + lane_base + ATT_COL_O + half * 32, o);
+    tmem_ld_wait();
+    if (q < p.Nq) {
+      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * ATT_D + half * 32;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tmem + lane_base + ATT_COL_O + c * 32, o);
-      tmem_ld_wait();
-      if (q < p.Nq) {
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * ATT_D + c * 32;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
-          reinterpret_cast<uint4*>(dst)[v] = u;
-        }
+      for (int v = 0; v < 4; ++v) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+        reinterpret_cast<uint4*>(dst)[v] = u;
       }
     }
   }
@@ -298,7 +308,7 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t smem_bytes = ATT_TILE_BYTES * (1 + 2 * ATT_STAGES) + 1024 + 128;
+  const size_t smem_bytes = ATT_TILE_BYTES * (1 + 2 * ATT_STAGES) + 1024 + 128 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -77,6 +77,7 @@ int concat_add(const void* a, int Ca, const void* b, int Cb, const void* c, void
                cudaStream_t stream);
 int axpy_bf16(const void* a, const void* b, void* y, float alpha, long long n, cudaStream_t stream);
 int silu_bf16(const void* x, void* y, long long n, cudaStream_t stream);
+int pad_channels(const void* x, void* y, int C, int Cpad, long long rows, cudaStream_t stream);
 int sinusoid_embedding(const float* t, void* out, int B, int dim, float max_period, int sin_first,
                        cudaStream_t stream);
 int conv3x3_small(const void* x, const void* w, const float* bias, const void* addend, void* y, int N, int H, int W,
@@ -183,6 +184,10 @@ int b200sr_concat_add(const void* a, int32_t Ca, const void* b, int32_t Cb, cons
 int b200sr_axpy_bf16(const void* a, const void* b, void* y, float alpha, int64_t n, void* stream) {
   if (a == nullptr || b == nullptr || y == nullptr) return B200SR_EINVAL;
   return axpy_bf16(a, b, y, alpha, n, S(stream));
+}
+int b200sr_pad_channels(const void* x, void* y, int32_t C, int32_t Cpad, int64_t rows, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return pad_channels(x, y, C, Cpad, rows, S(stream));
 }
 int b200sr_silu_bf16(const void* x, void* y, int64_t n, void* stream) {
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;

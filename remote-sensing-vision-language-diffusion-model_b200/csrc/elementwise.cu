@@ -161,6 +161,34 @@ int axpy_bf16(const void* a, const void* b, void* y, float alpha, long long n, c
 }
 
 // ------------------------------------------------------------------------------------------
+// y[rows, Cpad] = [x[rows, C] | 0]: pads the latent's 4 channels to one 64-channel K chunk so the
+// stem convolutions run on the tensor-core implicit-GEMM path.
+// ------------------------------------------------------------------------------------------
+__global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int Cpad,
+                                    size_t rows) {
+  const int V = Cpad / 8;
+  const size_t total = rows * V;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / V;
+    const int c0 = static_cast<int>(i - row * V) * 8;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? x[row * C + c0 + j] : __float2bfloat16(0.f);
+    reinterpret_cast<uint4*>(y)[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+int pad_channels(const void* x, void* y, int C, int Cpad, long long rows, cudaStream_t stream) {
+  if (C <= 0 || Cpad < C || (Cpad % 8) || rows <= 0) return B200SR_EINVAL;
+  const size_t total = static_cast<size_t>(rows) * (Cpad / 8);
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  pad_channels_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                reinterpret_cast<__nv_bfloat16*>(y), C, Cpad, static_cast<size_t>(rows));
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------
 // SiLU on a small fp32/bf16 vector (embedding path), bf16 out
 // ------------------------------------------------------------------------------------------
 __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {

@@ -132,6 +132,12 @@ def axpy(a, b, alpha=1.0):
     return (a.float() + alpha * b.float()).to(bf16)
 
 
+def pad_channels(x, cpad):
+    y = torch.zeros(*x.shape[:-1], cpad, dtype=bf16)
+    y[..., : x.shape[-1]] = x
+    return y
+
+
 def silu(x):
     return F.silu(x.float()).to(bf16)
 
