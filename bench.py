@@ -200,6 +200,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     eager.cond = eng.cond
     eager.step(x, step_i, noise, 0.0)
     recs = []
+    torch.cuda.synchronize()
+    # Keep the GPU busy (~80 ms spin) while the host enqueues the whole step, so the per-launch event
+    # pairs bracket back-to-back kernels and not host launch latency.
+    torch.cuda._sleep(int(0.08 * 1.9e9))
     ops.set_profile(recs)
     eager.step(x, step_i, noise, 0.0)
     ops.set_profile(None)

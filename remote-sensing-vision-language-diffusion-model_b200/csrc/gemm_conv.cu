@@ -17,9 +17,16 @@
 // warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Two accumulator
 // stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1.
 //
+// With one 128 x BN tile per SM the mainloop is shared-memory-bandwidth bound (TMA writes plus the
+// SS-mode operand reads need ~190 B/cycle/SM against 128 available; measured 40-50 % tensor-pipe
+// activity, and TMA multicast of the weight tile inside a 2-CTA cluster changed nothing), so CTAs
+// run as CTA pairs (kCluster = 2, tcgen05 cta_group::2): one 256 x BN UMMA spans both SMs, each
+// CTA stages its own 128 rows of A and only HALF of the weight tile, and the leader CTA issues
+// the MMAs for both.  Problems with a single M block use kCluster = 1 (cta_group::1).
+//
 // Fused epilogues: +bias[N], +rowvec[group, N] (ResBlock timestep-embedding add, one group per
-// image), alpha scale, +residual[M, N], GEGLU (value/gate interleaved in 16-column groups by the
-// weight packer), bf16 or fp32 output.
+// image), alpha scale, +residual[M, N], SiLU, GEGLU (value/gate interleaved in 16-column groups by
+// the weight packer), bf16 or fp32 output.
 #include "common.cuh"
 
 namespace b200sr {
@@ -37,7 +44,7 @@ struct GemmParams {
   int mode;
   int M, N, K;
   int BN;
-  int num_m_blocks, num_n_blocks;
+  int num_m_blocks, num_n_blocks;  // num_m_blocks is rounded up to a multiple of the cluster size
   int k_iters;
   int kc_per_tap;
   int Cin;
@@ -59,17 +66,93 @@ struct GemmParams {
   int act;
 };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile loads of a CTA pair: data lands in the issuing CTA's smem, the bytes are counted on the
+// mbarrier at `bar_addr`, which may live in the peer (leader) CTA.
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem2_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int kCluster>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // Round the dynamic smem base up to 1024 B (swizzle-128B atoms are 1024 B aligned).
+  // Round the dynamic smem base up to 1024 B (swizzle-128B atoms are 1024 B aligned).  The
+  // offset is identical in both CTAs of a cluster (same kernel, same static layout), which the
+  // multicast relies on.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = A_STAGE_BYTES + p.BN * (BLOCK_K * 2);
+  // per-CTA stage: 128 rows of A and this CTA's BN / kCluster rows of the weight tile
+  const int stage_bytes = A_STAGE_BYTES + (p.BN / kCluster) * (BLOCK_K * 2);
   const int stages = p.stages;
+  const uint32_t rank = kCluster > 1 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -81,25 +164,35 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // leader's expect_tx arrive; bytes of both CTAs are counted here
+      mbar_init(&empty_bar[s], 1);  // one (multicast) commit from the MMA issuer
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], 4 * kCluster);  // one arrive per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (kCluster == 1) {
+      tmem_alloc(tmem_base_slot, TMEM_COLS);
+      tmem_relinquish();
+    } else {
+      tmem2_alloc(tmem_base_slot, TMEM_COLS);
+      tmem2_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // peer barriers / TMEM must exist before remote arrives and pair MMAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  // Work = "cluster tiles": kCluster consecutive M blocks x one N block.
+  const int m_groups = p.num_m_blocks / kCluster;
+  const int num_work = m_groups * p.num_n_blocks;
+  const int work0 = blockIdx.x / kCluster;
+  const int work_stride = gridDim.x / kCluster;
   const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
 
   if (warp == 0) {
@@ -107,11 +200,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
-        const int n0 = n_blk * p.BN;
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes) * kCluster;
+      const int b_rows = p.BN / kCluster;
+      for (int work = work0; work < num_work; work += work_stride) {
+        const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
+        const int n_blk = work / m_groups;
+        const int n0 = n_blk * p.BN + static_cast<int>(rank) * b_rows;  // this CTA's rows of the weight tile
         int w0 = 0, h0 = 0, i0 = 0;
         if (p.mode != 0) {
           const int tw = m_blk % p.tiles_w;
@@ -125,22 +219,37 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+          int kb;  // K coordinate of the weight tile
+          int tap = 0, c0 = 0, kh = 0, kw = 0;
           if (p.mode == 0) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], it * BLOCK_K, m_blk * BLOCK_M);
-            tma_load_2d(sb, &tmB, &full_bar[stage], it * BLOCK_K, n0);
+            kb = it * BLOCK_K;
           } else {
-            const int tap = it / p.kc_per_tap;
-            const int c0 = (it - tap * p.kc_per_tap) * BLOCK_K;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            if (p.mode == 1) {
+            tap = it / p.kc_per_tap;
+            c0 = (it - tap * p.kc_per_tap) * BLOCK_K;
+            kh = tap / 3;
+            kw = tap - kh * 3;
+            kb = tap * p.Cin + c0;
+          }
+          // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
+          const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
+          if (kCluster == 1) {
+            if (p.mode == 0)
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb, m_blk * BLOCK_M);
+            else if (p.mode == 1)
               tma_load_4d(sa, &tmA, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, i0);
-            } else {
-              // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
-              const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
+            else
               tma_load_5d(sa, &tmA, &full_bar[stage], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
-            }
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + c0, n0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb, n0);
+          } else {
+            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+            if (p.mode == 0)
+              tma2_load_2d(sa, &tmA, bar, kb, m_blk * BLOCK_M);
+            else if (p.mode == 1)
+              tma2_load_4d(sa, &tmA, bar, c0, w0 + kw - 1, h0 + kh - 1, i0);
+            else
+              tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+            tma2_load_2d(sb, &tmB, bar, kb, n0);
           }
           if (++stage == stages) {
             stage = 0;
@@ -151,13 +260,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, static_cast<uint32_t>(p.BN), 0, 0);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M * kCluster, static_cast<uint32_t>(p.BN), 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = work0; work < num_work; work += work_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STAGE_COLS;
@@ -171,15 +280,26 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            if (kCluster == 1)
+              umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            else
+              umma2_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // free the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (kCluster == 1)
+            umma_commit(&empty_bar[stage]);
+          else
+            umma2_commit_mc(&empty_bar[stage], 3);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs of a pair)
+        if (kCluster == 1)
+          umma_commit(&tmem_full[acc]);
+        else
+          umma2_commit_mc(&tmem_full[acc], 3);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -192,9 +312,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = sub * 32 + lane;      // accumulator row == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+    for (int work = work0; work < num_work; work += work_stride) {
+      const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
+      const int n_blk = work / m_groups;
       const int n0 = n_blk * p.BN;
       long long row;
       int group;
@@ -311,7 +431,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kCluster == 1)
+          mbar_arrive(&tmem_empty[acc]);
+        else
+          mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));  // the leader's MMA thread waits on it
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -321,8 +446,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // the pair's MMAs / remote arrives must be finished in both CTAs
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) {
+    if (kCluster == 1)
+      tmem_dealloc(tmem_base, TMEM_COLS);
+    else
+      tmem2_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -334,32 +465,35 @@ static int ilog2_exact(int v) {
   return ((1 << l) == v) ? l : -1;
 }
 
-// Pick the N tile: minimise waves x per-tile cost.  Per-k16 step cost is the slower of the MMA
-// (BN/2 cycles at M=128) and the shared-memory operand reads ((4 KiB + BN*32 B) / 128 B/cycle).
-static int pick_bn(int m_blocks, int N, int k_iters, int sms, int geglu) {
+// Pick the N tile: minimise waves x per-tile cost.  Per k-iteration (K = 64) a CTA is bounded by
+// the MMA (4 x BN/2 cycles) and by shared-memory traffic: TMA writes + SS-mode operand reads of
+// its A tile and its share of the weight tile, 2 x (16 KiB + BN*128/cluster B) at 128 B/cycle.
+static int pick_bn(int m_blocks, int N, int k_iters, int sms, int cluster) {
   int best = 128;
   double best_cost = 1e30;
+  const int slots = sms / cluster;
+  const int m_groups = (m_blocks + cluster - 1) / cluster;
   for (int bn = 32; bn <= 256; bn += 32) {
     if (bn > ((N + 31) / 32) * 32 && bn != 32) continue;
     const int n_blocks = (N + bn - 1) / bn;
-    const long long tiles = static_cast<long long>(m_blocks) * n_blocks;
-    const long long waves = (tiles + sms - 1) / sms;
-    const double step = fmax(bn / 2.0, 32.0 + bn / 4.0);
-    const double tile_cost = 4.0 * step * k_iters + 600.0 + bn * 6.0;  // mainloop + fill/drain + epilogue tail
+    const long long work = static_cast<long long>(m_groups) * n_blocks;
+    const long long waves = (work + slots - 1) / slots;
+    const double mma = 4.0 * (bn / 2.0);
+    const double smem = 2.0 * (16384.0 + bn * 128.0 / cluster) / 128.0;
+    const double tile_cost = fmax(mma, smem) * k_iters + 2500.0 + bn * 8.0;
     const double cost = waves * tile_cost;
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
     }
   }
-  (void)geglu;
   return best;
 }
 
-
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+template <int kCluster>
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
-  const int stage_bytes = A_STAGE_BYTES + p.BN * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + (p.BN / kCluster) * BLOCK_K * 2;
   int stages = smem_budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.k_iters + 1) stages = p.k_iters + 1;
@@ -368,15 +502,28 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p,
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
       return B200SR_ELAUNCH;
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_conv_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
-  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+  const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
+  const int slots = num_sms() / kCluster;
+  const int grid = (work < slots ? work : slots) * kCluster;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_conv_kernel<kCluster>, tmA, tmB, p);
+  return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
 static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
@@ -399,6 +546,23 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   return B200SR_OK;
 }
 
+// Shared tail of both entry points: choose cluster / BN, encode the weight map, launch.
+static int finish(const CUtensorMap& tmA, const void* W, GemmParams& p, int real_m_blocks, int force_bn,
+                  cudaStream_t stream) {
+  const int cluster = real_m_blocks >= 2 ? 2 : 1;
+  p.num_m_blocks = ((real_m_blocks + cluster - 1) / cluster) * cluster;
+  p.BN = force_bn > 0 ? force_bn : pick_bn(real_m_blocks, p.N, p.k_iters, num_sms(), cluster);
+  if (p.BN % 32 != 0 || p.BN > 256 || p.BN <= 0) return B200SR_EINVAL;
+  p.num_n_blocks = (p.N + p.BN - 1) / p.BN;
+  CUtensorMap tmB;
+  uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+  uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
+  uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN / cluster)};
+  const int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
+  if (rc) return rc;
+  return cluster == 2 ? launch_t<2>(tmA, tmB, p, stream) : launch_t<1>(tmA, tmB, p, stream);
+}
+
 int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, const EpilogueArgs& e, int force_bn,
               cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (lda % 8) != 0) return B200SR_EINVAL;
@@ -407,29 +571,16 @@ int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, 
   p.M = M;
   p.N = N;
   p.K = K;
-  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
   p.k_iters = (K + BLOCK_K - 1) / BLOCK_K;
-  p.BN = force_bn > 0 ? force_bn : pick_bn(p.num_m_blocks, N, p.k_iters, num_sms(), e.geglu);
-  if (p.BN % 32 != 0 || p.BN > 256) return B200SR_EINVAL;
-  p.num_n_blocks = (N + p.BN - 1) / p.BN;
   int rc = fill_epilogue(p, e);
   if (rc) return rc;
-  CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
-    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
-    uint32_t box[2] = {BLOCK_K, BLOCK_M};
-    rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
-    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN)};
-    rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  return launch(tmA, tmB, p, stream);
+  CUtensorMap tmA;
+  uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+  uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+  uint32_t box[2] = {BLOCK_K, BLOCK_M};
+  rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
+  if (rc) return rc;
+  return finish(tmA, W, p, (M + BLOCK_M - 1) / BLOCK_M, force_bn, stream);
 }
 
 // x: NHWC bf16 [NB, H, W, Cin]; w: [Cout, 3, 3, Cin] bf16 (K = tap*Cin + c); stride 1 or 2, pad 1.
@@ -461,15 +612,11 @@ int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, in
   p.tiles_w = OW / bw;
   p.tiles_h = (OH + bh - 1) / bh;
   p.tiles_n = (NB + bn - 1) / bn;
-  p.num_m_blocks = p.tiles_w * p.tiles_h * p.tiles_n;
   p.kc_per_tap = Cin / BLOCK_K;
   p.k_iters = 9 * p.kc_per_tap;
-  p.BN = force_bn > 0 ? force_bn : pick_bn(p.num_m_blocks, Cout, p.k_iters, num_sms(), 0);
-  if (p.BN % 32 != 0 || p.BN > 256) return B200SR_EINVAL;
-  p.num_n_blocks = (Cout + p.BN - 1) / p.BN;
   int rc = fill_epilogue(p, e);
   if (rc) return rc;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA;
   if (stride == 1) {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                         static_cast<uint64_t>(NB)};
@@ -487,14 +634,8 @@ int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, in
     rc = make_tmap_bf16(&tmA, x, 5, dims, strides, box);
   }
   if (rc) return rc;
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(9) * Cin, static_cast<uint64_t>(Cout)};
-    uint64_t strides[1] = {static_cast<uint64_t>(9) * Cin * 2};
-    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN)};
-    rc = make_tmap_bf16(&tmB, w, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  return launch(tmA, tmB, p, stream);
+  // Out-of-range spatial tiles (cluster round-up) decode to tn >= tiles_n: all rows masked, loads zero-filled.
+  return finish(tmA, w, p, p.tiles_w * p.tiles_h * p.tiles_n, force_bn, stream);
 }
 
 }  // namespace b200sr
