@@ -101,10 +101,12 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
+      pdl_wait();  // Q, K, V are produced by the previous kernel
       mbar_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_3d(sQ, &tmQ, q_full, p.q_col + h * ATT_D, q0, b);
       int stage = 0;
@@ -317,8 +319,9 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
     attr_set = true;
   }
   dim3 grid((Nq + ATT_BM - 1) / ATT_BM, H, B);
-  attention_d64_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
-  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+  return launch_k(attention_d64_kernel, grid, dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmK, tmV, p) == cudaSuccess
+             ? B200SR_OK
+             : B200SR_ELAUNCH;
 }
 
 }  // namespace b200sr

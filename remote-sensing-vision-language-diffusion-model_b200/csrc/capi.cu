@@ -1,5 +1,7 @@
 // b200sr — extern "C" entry points (include/b200sr.h) and shared host utilities.
 #include "../../include/b200sr.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200sr {
@@ -17,6 +19,15 @@ PFN_encodeTiled get_encode_tiled() {
       fn = reinterpret_cast<PFN_encodeTiled>(p);
   }
   return fn;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200SR_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

@@ -218,6 +218,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t m, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the step is launched with the programmatic
+// stream-serialisation attribute, lets its successor start launching immediately
+// (pdl_launch_dependents) and waits for its predecessor's results (pdl_wait) only after its own
+// prologue (barrier init, TMEM allocation, descriptor / weight prefetch).  pdl_wait must be
+// executed by every thread before it touches memory written by earlier kernels.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // small numeric helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
@@ -249,6 +259,35 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
+bool pdl_enabled();  // B200SR_PDL=0 disables programmatic dependent launch (debugging)
+
+// Launch with the PDL attribute (and an optional cluster size along x).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            int cluster, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Encode a bf16 tensor map with 128B swizzle. dims/strides innermost first; strides in bytes
 // for dims 1..rank-1.  Returns 0 or a negative error code.

@@ -23,6 +23,8 @@ namespace b200sr {
 // ------------------------------------------------------------------------------------------
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int HW,
                                              float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -40,6 +42,8 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
 }
 
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -59,13 +63,13 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x
 int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int HW, float scale, cudaStream_t stream) {
   if (N <= 0 || C <= 0 || HW <= 0) return B200SR_EINVAL;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), C, HW, scale);
+  launch_k(nchw_f32_to_nhwc_bf16_kernel, dim3(grid), dim3(block), 0, stream, 1, x, reinterpret_cast<__nv_bfloat16*>(y), C, HW, scale);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStream_t stream) {
   if (N <= 0 || C <= 0 || HW <= 0) return B200SR_EINVAL;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, C, HW);
+  launch_k(nhwc_bf16_to_nchw_f32_kernel, dim3(grid), dim3(block), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x), y, C, HW);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
@@ -74,6 +78,8 @@ int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStr
 // ------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C8,
                                   size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % C8);
@@ -90,7 +96,7 @@ int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStre
   const size_t total = static_cast<size_t>(N) * 4 * H * W * (C / 8);
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  upsample2x_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W,
+  launch_k(upsample2x_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W,
                                               C / 8, total);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
@@ -100,6 +106,8 @@ int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStre
 // ------------------------------------------------------------------------------------------
 __global__ void concat_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ c,
                                   uint4* __restrict__ out, int Ca8, int Cb8, size_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ct8 = Ca8 + Cb8;
   const size_t total = rows * Ct8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -132,7 +140,7 @@ int concat_add(const void* a, int Ca, const void* b, int Cb, const void* c, void
   const size_t total = static_cast<size_t>(rows) * ((Ca + Cb) / 8);
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  concat_add_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+  launch_k(concat_add_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
                                               reinterpret_cast<const uint4*>(c), reinterpret_cast<uint4*>(out), Ca / 8,
                                               Cb / 8, static_cast<size_t>(rows));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
@@ -143,6 +151,8 @@ int concat_add(const void* a, int Ca, const void* b, int Cb, const void* c, void
 // ------------------------------------------------------------------------------------------
 __global__ void axpy_bf16_kernel(const __nv_bfloat162* __restrict__ a, const __nv_bfloat162* __restrict__ b,
                                  __nv_bfloat162* __restrict__ y, float alpha, size_t n2) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float2 f = __bfloat1622float2(a[i]), g = __bfloat1622float2(b[i]);
@@ -154,7 +164,7 @@ int axpy_bf16(const void* a, const void* b, void* y, float alpha, long long n, c
   const size_t n2 = static_cast<size_t>(n) / 2;
   int grid = static_cast<int>((n2 + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  axpy_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat162*>(a),
+  launch_k(axpy_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat162*>(a),
                                              reinterpret_cast<const __nv_bfloat162*>(b),
                                              reinterpret_cast<__nv_bfloat162*>(y), alpha, n2);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
@@ -166,6 +176,8 @@ int axpy_bf16(const void* a, const void* b, void* y, float alpha, long long n, c
 // ------------------------------------------------------------------------------------------
 __global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int Cpad,
                                     size_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int V = Cpad / 8;
   const size_t total = rows * V;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -183,7 +195,7 @@ int pad_channels(const void* x, void* y, int C, int Cpad, long long rows, cudaSt
   const size_t total = static_cast<size_t>(rows) * (Cpad / 8);
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  pad_channels_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_k(pad_channels_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x),
                                                 reinterpret_cast<__nv_bfloat16*>(y), C, Cpad, static_cast<size_t>(rows));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
@@ -192,6 +204,8 @@ int pad_channels(const void* x, void* y, int C, int Cpad, long long rows, cudaSt
 // SiLU on a small fp32/bf16 vector (embedding path), bf16 out
 // ------------------------------------------------------------------------------------------
 __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
@@ -200,7 +214,7 @@ int silu_bf16(const void* x, void* y, long long n, cudaStream_t stream) {
   if (n <= 0) return B200SR_EINVAL;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  silu_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_k(silu_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x),
                                              reinterpret_cast<__nv_bfloat16*>(y), static_cast<size_t>(n));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
@@ -211,6 +225,8 @@ int silu_bf16(const void* x, void* y, long long n, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 __global__ void sinusoid_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim,
                                 float max_period, int sin_first) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -227,7 +243,7 @@ int sinusoid_embedding(const float* t, void* out, int B, int dim, float max_peri
                        cudaStream_t stream) {
   if (B <= 0 || dim < 2) return B200SR_EINVAL;
   const int total = B * (dim / 2);
-  sinusoid_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, reinterpret_cast<__nv_bfloat16*>(out), B, dim, max_period,
+  launch_k(sinusoid_kernel, dim3((total + 127) / 128), dim3(128), 0, stream, 1, t, reinterpret_cast<__nv_bfloat16*>(out), B, dim, max_period,
                                                            sin_first);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
@@ -241,6 +257,8 @@ int sinusoid_embedding(const float* t, void* out, int B, int dim, float max_peri
 __global__ void conv3x3_few_in_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                       const float* __restrict__ bias, const __nv_bfloat16* __restrict__ addend,
                                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int Cin, int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread = one output pixel x 8 output channels; weights staged in smem as fp32
   extern __shared__ float s_w[];  // [Cout][9*Cin]
   const int K = 9 * Cin;
@@ -298,6 +316,8 @@ template <int COUT>
 __global__ void conv3x3_few_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                        const float* __restrict__ bias, void* __restrict__ y, int N, int H, int W,
                                        int Cin, int out_nchw_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one warp = one output pixel; lanes stride over (tap, channel-vector); warp-shuffle reduction
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -368,7 +388,7 @@ int conv3x3_small(const void* x, const void* w, const float* bias, const void* a
     const size_t total = static_cast<size_t>(N) * H * W * (Cout / 8);
     int grid = static_cast<int>((total + 255) / 256);
     if (grid > num_sms() * 4) grid = num_sms() * 4;
-    conv3x3_few_in_kernel<<<grid, 256, smem, stream>>>(xi, wi, bias, reinterpret_cast<const __nv_bfloat16*>(addend),
+    launch_k(conv3x3_few_in_kernel, dim3(grid), dim3(256), smem, stream, 1, xi, wi, bias, reinterpret_cast<const __nv_bfloat16*>(addend),
                                                        reinterpret_cast<__nv_bfloat16*>(y), N, H, W, Cin, Cout);
   } else if (Cout <= 4 && (Cin % 8) == 0) {
     if (addend != nullptr) return B200SR_EINVAL;
@@ -376,10 +396,10 @@ int conv3x3_small(const void* x, const void* w, const float* bias, const void* a
     int grid = static_cast<int>((total + 7) / 8);
     if (grid > num_sms() * 32) grid = num_sms() * 32;
     switch (Cout) {
-      case 1: conv3x3_few_out_kernel<1><<<grid, 256, 0, stream>>>(xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
-      case 2: conv3x3_few_out_kernel<2><<<grid, 256, 0, stream>>>(xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
-      case 3: conv3x3_few_out_kernel<3><<<grid, 256, 0, stream>>>(xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
-      default: conv3x3_few_out_kernel<4><<<grid, 256, 0, stream>>>(xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
+      case 1: launch_k(conv3x3_few_out_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
+      case 2: launch_k(conv3x3_few_out_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
+      case 3: launch_k(conv3x3_few_out_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
+      default: launch_k(conv3x3_few_out_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, xi, wi, bias, y, N, H, W, Cin, out_nchw_f32); break;
     }
   } else {
     return B200SR_EINVAL;
@@ -397,6 +417,8 @@ int conv3x3_small(const void* x, const void* w, const float* bias, const void* a
 __global__ void sampler_pre_kernel(const float* __restrict__ x, const float* __restrict__ noise,
                                    const float* __restrict__ sc, float* __restrict__ x_hat,
                                    __nv_bfloat16* __restrict__ net_in, int B, int C, int HW, int cfg_copies) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(B) * C * HW;
   const float sigma = sc[0], sigma_hat = sc[1], sigma_q = sc[3], s_noise = sc[5];
   const float churn = sqrtf(fmaxf(sigma_hat * sigma_hat - sigma * sigma, 0.f)) * s_noise;
@@ -420,7 +442,7 @@ int sampler_pre(const float* x, const float* noise, const float* scalars, float*
   const size_t total = static_cast<size_t>(B) * C * HW;
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  sampler_pre_kernel<<<grid, 256, 0, stream>>>(x, noise, scalars, x_hat, reinterpret_cast<__nv_bfloat16*>(net_in), B, C,
+  launch_k(sampler_pre_kernel, dim3(grid), dim3(256), 0, stream, 1, x, noise, scalars, x_hat, reinterpret_cast<__nv_bfloat16*>(net_in), B, C,
                                                HW, cfg_copies);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
@@ -435,6 +457,8 @@ int sampler_pre(const float* x, const float* noise, const float* scalars, float*
 __global__ void sampler_post_kernel(const float* __restrict__ eps, const float* __restrict__ x_hat,
                                     const float* __restrict__ sc, float* __restrict__ denoised_out,
                                     float* __restrict__ x_next, int B, int C, int HW, int use_cfg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(B) * C * HW;
   const float sigma_hat = sc[1], sigma_next = sc[2], sigma_q = sc[3], cfg = sc[4];
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -459,13 +483,15 @@ int sampler_post(const float* eps, const float* x_hat, const float* scalars, flo
   const size_t total = static_cast<size_t>(B) * C * HW;
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  sampler_post_kernel<<<grid, 256, 0, stream>>>(eps, x_hat, scalars, denoised_out, x_next, B, C, HW, use_cfg);
+  launch_k(sampler_post_kernel, dim3(grid), dim3(256), 0, stream, 1, eps, x_hat, scalars, denoised_out, x_next, B, C, HW, use_cfg);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
 // Euler update from an already guided `denoised` (cache-hit path reuses the previous one).
 __global__ void euler_from_denoised_kernel(const float* __restrict__ den, const float* __restrict__ x_hat,
                                            const float* __restrict__ sc, float* __restrict__ x_next, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float sigma_hat = sc[1], sigma_next = sc[2];
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -479,7 +505,7 @@ int euler_from_denoised(const float* denoised, const float* x_hat, const float* 
   if (n <= 0) return B200SR_EINVAL;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  euler_from_denoised_kernel<<<grid, 256, 0, stream>>>(denoised, x_hat, scalars, x_next, static_cast<size_t>(n));
+  launch_k(euler_from_denoised_kernel, dim3(grid), dim3(256), 0, stream, 1, denoised, x_hat, scalars, x_next, static_cast<size_t>(n));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
@@ -490,6 +516,8 @@ int euler_from_denoised(const float* denoised, const float* x_hat, const float* 
 __global__ void tile_accumulate_kernel(const float* __restrict__ tile, const float* __restrict__ weight,
                                        float* __restrict__ acc, float* __restrict__ cnt, int BC, int th, int tw, int H,
                                        int W, int h0, int w0) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(BC) * th * tw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -504,6 +532,8 @@ __global__ void tile_accumulate_kernel(const float* __restrict__ tile, const flo
 }
 __global__ void tile_normalize_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
                                       float* __restrict__ out, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     out[i] = acc[i] / cnt[i];
@@ -514,14 +544,14 @@ int tile_accumulate(const float* tile, const float* weight, float* acc, float* c
   const size_t total = static_cast<size_t>(BC) * th * tw;
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  tile_accumulate_kernel<<<grid, 256, 0, stream>>>(tile, weight, acc, cnt, BC, th, tw, H, W, h0, w0);
+  launch_k(tile_accumulate_kernel, dim3(grid), dim3(256), 0, stream, 1, tile, weight, acc, cnt, BC, th, tw, H, W, h0, w0);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 int tile_normalize(const float* acc, const float* cnt, float* out, long long n, cudaStream_t stream) {
   if (n <= 0) return B200SR_EINVAL;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  tile_normalize_kernel<<<grid, 256, 0, stream>>>(acc, cnt, out, static_cast<size_t>(n));
+  launch_k(tile_normalize_kernel, dim3(grid), dim3(256), 0, stream, 1, acc, cnt, out, static_cast<size_t>(n));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
@@ -532,6 +562,8 @@ int tile_normalize(const float* acc, const float* cnt, float* out, long long n, 
 // ------------------------------------------------------------------------------------------
 __global__ void rel_l1_partial_kernel(const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ cur,
                                       double* __restrict__ sums, size_t n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   float a = 0.f, b = 0.f;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -567,6 +599,8 @@ __global__ void rel_l1_partial_kernel(const __nv_bfloat16* __restrict__ prev, co
 }
 __global__ void rel_l1_finalize_kernel(double* __restrict__ sums, const float* __restrict__ threshold,
                                        float* __restrict__ result, double n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double mean_diff = sums[0] / n, mean_prev = sums[1] / n;
   const float diff = static_cast<float>(mean_diff / (mean_prev + 1e-6));
   result[0] = diff;
@@ -581,9 +615,9 @@ int rel_l1_similarity(const void* prev, const void* cur, long long n, const floa
   const size_t n8 = static_cast<size_t>(n) / 8;
   int grid = static_cast<int>((n8 + 255) / 256);
   if (grid > num_sms() * 4) grid = num_sms() * 4;
-  rel_l1_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(prev),
+  launch_k(rel_l1_partial_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(prev),
                                                   reinterpret_cast<const __nv_bfloat16*>(cur), workspace, n8);
-  rel_l1_finalize_kernel<<<1, 1, 0, stream>>>(workspace, threshold, result, static_cast<double>(n));
+  launch_k(rel_l1_finalize_kernel, dim3(1), dim3(1), 0, stream, 1, workspace, threshold, result, static_cast<double>(n));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
@@ -596,6 +630,8 @@ int rel_l1_similarity(const void* prev, const void* cur, long long n, const floa
 __global__ void sr3_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                                   const float* __restrict__ noise, const float* __restrict__ sc, float* __restrict__ out,
                                   size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float cr = sc[0], crm1 = sc[1], c1 = sc[2], c2 = sc[3], std = expf(0.5f * sc[4]);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -612,7 +648,7 @@ int sr3_update(const float* x, const float* eps, const float* noise, const float
   if (n <= 0) return B200SR_EINVAL;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  sr3_update_kernel<<<grid, 256, 0, stream>>>(x, eps, noise, scalars, out, static_cast<size_t>(n));
+  launch_k(sr3_update_kernel, dim3(grid), dim3(256), 0, stream, 1, x, eps, noise, scalars, out, static_cast<size_t>(n));
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

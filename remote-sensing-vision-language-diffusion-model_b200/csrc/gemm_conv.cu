@@ -187,6 +187,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (kCluster > 1) cluster_sync_all();  // peer barriers / TMEM must exist before remote arrives and pair MMAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_launch_dependents();  // the next kernel may start its own prologue now
 
   // Work = "cluster tiles": kCluster consecutive M blocks x one N block.
   const int m_groups = p.num_m_blocks / kCluster;
@@ -215,18 +216,29 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           h0 = th * bh;
           i0 = tn << p.bn_log2;
         }
-        for (int it = 0; it < p.k_iters; ++it) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * stage_bytes;
+        // Weights never depend on the previous kernel: on the first tile their first `stages` chunks are
+        // requested before griddepcontrol.wait, the activation (A) chunks after it.
+        const bool first = (work == work0);
+        const int pre = first ? (p.k_iters < stages ? p.k_iters : stages) : 0;
+        for (int it = 0; it < p.k_iters + pre; ++it) {
+          // it in [0, pre): weight chunk `it` only; it in [pre, 2*pre): activation chunk it-pre only;
+          // afterwards: both for chunk it-pre.
+          const bool w_only = it < pre, a_only = (it >= pre && it < 2 * pre);
+          const int kit = w_only ? it : it - pre;
+          if (it == pre && first) pdl_wait();
+          if (!first && it == 0) { /* later tiles: everything already ordered after the wait */ }
+          const int st = w_only || a_only ? kit : stage;
+          if (!w_only && !a_only) mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + st * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (leader && !a_only) mbar_expect_tx(&full_bar[st], tx_bytes);
           int kb;  // K coordinate of the weight tile
           int tap = 0, c0 = 0, kh = 0, kw = 0;
           if (p.mode == 0) {
-            kb = it * BLOCK_K;
+            kb = kit * BLOCK_K;
           } else {
-            tap = it / p.kc_per_tap;
-            c0 = (it - tap * p.kc_per_tap) * BLOCK_K;
+            tap = kit / p.kc_per_tap;
+            c0 = (kit - tap * p.kc_per_tap) * BLOCK_K;
             kh = tap / 3;
             kw = tap - kh * 3;
             kb = tap * p.Cin + c0;
@@ -234,23 +246,28 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
           const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
           if (kCluster == 1) {
-            if (p.mode == 0)
-              tma_load_2d(sa, &tmA, &full_bar[stage], kb, m_blk * BLOCK_M);
-            else if (p.mode == 1)
-              tma_load_4d(sa, &tmA, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, i0);
-            else
-              tma_load_5d(sa, &tmA, &full_bar[stage], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb, n0);
+            if (!w_only) {
+              if (p.mode == 0)
+                tma_load_2d(sa, &tmA, &full_bar[st], kb, m_blk * BLOCK_M);
+              else if (p.mode == 1)
+                tma_load_4d(sa, &tmA, &full_bar[st], c0, w0 + kw - 1, h0 + kh - 1, i0);
+              else
+                tma_load_5d(sa, &tmA, &full_bar[st], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+            }
+            if (!a_only) tma_load_2d(sb, &tmB, &full_bar[st], kb, n0);
           } else {
-            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
-            if (p.mode == 0)
-              tma2_load_2d(sa, &tmA, bar, kb, m_blk * BLOCK_M);
-            else if (p.mode == 1)
-              tma2_load_4d(sa, &tmA, bar, c0, w0 + kw - 1, h0 + kh - 1, i0);
-            else
-              tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
-            tma2_load_2d(sb, &tmB, bar, kb, n0);
+            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[st]), 0);  // the leader's barrier
+            if (!w_only) {
+              if (p.mode == 0)
+                tma2_load_2d(sa, &tmA, bar, kb, m_blk * BLOCK_M);
+              else if (p.mode == 1)
+                tma2_load_4d(sa, &tmA, bar, c0, w0 + kw - 1, h0 + kh - 1, i0);
+              else
+                tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+            }
+            if (!a_only) tma2_load_2d(sb, &tmB, bar, kb, n0);
           }
+          if (w_only) continue;  // the ring position advances once per chunk (with its activation load)
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -510,19 +527,8 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
   const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
   const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_conv_kernel<kCluster>, tmA, tmB, p);
+  const cudaError_t err = launch_k(gemm_conv_kernel<kCluster>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream,
+                                   kCluster, tmA, tmB, p);
   return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

@@ -21,6 +21,8 @@ namespace b200sr {
 __global__ void __launch_bounds__(1024)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
                 int pix_per_cta, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_red[];  // [P][C] sums, then [P][C] sums of squares (no atomics: deterministic)
   const int C8 = C >> 3;
   const int P = blockDim.x / C8;
@@ -111,6 +113,8 @@ struct GnApplyArgs {
 };
 
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_ab[];  // [groups] mean, [groups] rstd
   const int C = a.C, HW = a.HW;
   const int C8 = C >> 3;
@@ -232,7 +236,7 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   int threads, P, ppc, chunks;
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
   dim3 grid(chunks, N);
-  gn_stats_kernel<<<grid, threads, 2 * static_cast<size_t>(P) * C * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * static_cast<size_t>(P) * C * sizeof(float), stream, 1, reinterpret_cast<const __nv_bfloat16*>(x),
                                                                     workspace, HW, C, groups, ppc, chunks);
   GnApplyArgs a;
   a.x = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -251,7 +255,7 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   a.pix_per_cta = ppc;
   a.chunks_stats = chunks;
   a.silu = silu;
-  gn_apply_kernel<<<grid, threads, 2 * groups * sizeof(float), stream>>>(a);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 2 * groups * sizeof(float), stream, 1, a);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
@@ -263,6 +267,8 @@ template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                   const float* __restrict__ weight, const float* __restrict__ bias, int M, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= M) return;
@@ -335,15 +341,15 @@ int layer_norm(const void* x, void* y, const float* weight, const float* bias, i
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   const int vpl = (C / 8 + 31) / 32;
   if (vpl <= 1)
-    layer_norm_kernel<1><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+    launch_k(layer_norm_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, xi, yo, weight, bias, M, C, eps);
   else if (vpl <= 3)
-    layer_norm_kernel<3><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+    launch_k(layer_norm_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, xi, yo, weight, bias, M, C, eps);
   else if (vpl <= 5)
-    layer_norm_kernel<5><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+    launch_k(layer_norm_kernel<5>, dim3(grid), dim3(256), 0, stream, 1, xi, yo, weight, bias, M, C, eps);
   else if (vpl <= 10)
-    layer_norm_kernel<10><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+    launch_k(layer_norm_kernel<10>, dim3(grid), dim3(256), 0, stream, 1, xi, yo, weight, bias, M, C, eps);
   else
-    layer_norm_kernel<20><<<grid, 256, 0, stream>>>(xi, yo, weight, bias, M, C, eps);
+    launch_k(layer_norm_kernel<20>, dim3(grid), dim3(256), 0, stream, 1, xi, yo, weight, bias, M, C, eps);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
