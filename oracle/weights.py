@@ -15,9 +15,20 @@ from typing import Dict
 import torch
 
 
+# Output layers of residual branches.  The reference zero-initialises these in stage 2 (ResBlock conv2,
+# SpatialTransformer.proj_out, ZeroSFT zero_mul / zero_add / zero_conv, the control hint conv, UNet.out);
+# they are re-randomised at 1/4 of the default scale so the random network stays near the identity-
+# residual regime it is initialised in (at full scale a random-weight SDXL UNet amplifies the
+# unavoidable bf16 operand rounding of every layer to ~1e-2 on its own, leaving no room to judge the
+# kernels).  The SR3 residual ends (block2 conv, attention out conv) get the same treatment.
+BRANCH_END = (".out_layers.3.", ".proj_out.", ".zero_mul.", ".zero_add.", ".zero_conv.", ".input_hint_block.0.",
+              ".out.2.", ".block2.block.3.", ".attn.out.")
+BRANCH_END_GAIN = 0.25
+
+
 def fill_(sd: Dict[str, torch.Tensor], seed: int = 0) -> Dict[str, torch.Tensor]:
-    """In-place: weights ~ N(0, 1/(3 fan_in)) (the std of torch's default kaiming-uniform init),
-    biases ~ N(0, 0.02^2), norm scales ~ 1 + N(0, 0.05^2), norm shifts ~ N(0, 0.05^2)."""
+    """In-place: weights ~ N(0, 1/(3 fan_in)) (the std of torch's default kaiming-uniform init; x 1/4 for
+    BRANCH_END tensors), biases ~ N(0, 0.02^2), norm scales ~ 1 + N(0, 0.05^2), norm shifts ~ N(0, 0.05^2)."""
     for name in sorted(sd.keys()):
         t = sd[name]
         if not t.is_floating_point():
@@ -33,6 +44,8 @@ def fill_(sd: Dict[str, torch.Tensor], seed: int = 0) -> Dict[str, torch.Tensor]
         elif t.dim() >= 2:
             fan_in = t[0].numel()
             r = r * (1.0 / (3.0 * fan_in)) ** 0.5
+            if any(b in dotted for b in BRANCH_END):
+                r = r * BRANCH_END_GAIN
         else:
             r = r * 0.02
         with torch.no_grad():

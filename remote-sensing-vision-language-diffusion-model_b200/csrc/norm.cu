@@ -353,4 +353,36 @@ int layer_norm(const void* x, void* y, const float* weight, const float* bias, i
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
+// ------------------------------------------------------------------------------------------
+// Row softmax of an fp32 [rows, cols] score matrix -> bf16 probabilities (SR3 single-head
+// attention, models/sr3_model/sr3_modules/unet.py:133-138).  One warp per row, three passes
+// over an L2-resident row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int rows, int cols, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const float* src = x + static_cast<size_t>(row) * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, src[c]);
+  mx = warp_max(mx) * scale;
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += __expf(src[c] * scale - mx);
+  const float inv = 1.0f / warp_sum(sum);
+  __nv_bfloat16* dst = y + static_cast<size_t>(row) * cols;
+  for (int c = lane; c < cols; c += 32) dst[c] = __float2bfloat16(__expf(src[c] * scale - mx) * inv);
+}
+
+int softmax_rows(const float* x, void* y, int rows, int cols, float scale, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return B200SR_EINVAL;
+  const int grid = (rows + 7) / 8;
+  return launch_k(softmax_rows_kernel, dim3(grid), dim3(256), 0, stream, 1, x, reinterpret_cast<__nv_bfloat16*>(y), rows,
+                  cols, scale) == cudaSuccess
+             ? B200SR_OK
+             : B200SR_ELAUNCH;
+}
+
 }  // namespace b200sr

@@ -106,6 +106,10 @@ def attention(q, k, v, heads, *, q_col=0, k_col=0, v_col=0, scale=None):
     return (att @ vf).transpose(1, 2).reshape(b, nq, c).to(bf16)
 
 
+def softmax_rows(x, scale=1.0):
+    return torch.softmax(x.float() * scale, dim=-1).to(bf16)
+
+
 def nchw_to_nhwc_bf16(x, scale=1.0):
     return (x * scale).to(bf16).permute(0, 2, 3, 1).contiguous()
 
