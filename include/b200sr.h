@@ -95,9 +95,11 @@ int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* 
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
                          int32_t Nq, int32_t Nk, float scale, void* stream);
 
-/* y = softmax(x * scale) over the last dim; x fp32 [rows, cols], y bf16.  SR3 SelfAttention (one head of
- * width C, scores from b200sr_gemm_bf16 with fp32 output): models/sr3_model/sr3_modules/unet.py:133-138. */
-int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, float scale, void* stream);
+/* y = softmax(x * scale) over the first valid_cols entries of each row (the rest are written as 0: zero-
+ * padded keys); x fp32 [rows, cols], y bf16.  SR3 SelfAttention (one head of width C, scores from
+ * b200sr_gemm_bf16 with fp32 output): models/sr3_model/sr3_modules/unet.py:133-138. */
+int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t valid_cols, float scale,
+                        void* stream);
 
 /* Layout conversion at the nn.Module boundary. */
 int b200sr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, float scale, void* stream);

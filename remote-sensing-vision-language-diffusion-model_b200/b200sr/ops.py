@@ -310,12 +310,13 @@ def attention(
     return out
 
 
-def softmax_rows(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
-    """softmax(x * scale, dim=-1): fp32 [..., cols] -> bf16."""
+def softmax_rows(x: torch.Tensor, scale: float = 1.0, valid_cols: Optional[int] = None) -> torch.Tensor:
+    """softmax(x * scale) over the first `valid_cols` columns (others -> 0): fp32 [..., cols] -> bf16."""
     _req(x, torch.float32, "softmax_rows.x")
     cols = x.shape[-1]
     y = torch.empty(x.shape, dtype=bf16, device=x.device)
-    check(_lib.load().b200sr_softmax_rows(x.data_ptr(), y.data_ptr(), x.numel() // cols, cols, float(scale), _stream()),
+    check(_lib.load().b200sr_softmax_rows(x.data_ptr(), y.data_ptr(), x.numel() // cols, cols,
+                                          cols if valid_cols is None else valid_cols, float(scale), _stream()),
           "softmax_rows")
     return y
 

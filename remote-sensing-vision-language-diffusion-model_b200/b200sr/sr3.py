@@ -154,13 +154,19 @@ class SelfAttention(nn.Module, Packed):
         wq, wk, wv = self._pk("qkv", (self.qkv.weight,),
                               lambda t: tuple(p.contiguous() for p in ops.pack_linear(t).chunk(3, dim=0)))
         outs = []
+        t = h * w
+        tp = max(8, (t + 7) // 8 * 8)                              # GEMM dims must be multiples of 8
         for i in range(b):
             tok = n[i]                                             # [HW, C]
-            q, k = ops.gemm(tok, wq), ops.gemm(tok, wk)            # [HW, C]
-            v_t = ops.gemm(wv, tok)                                # [C, HW]  (V transposed: B operand of P @ V)
-            s = ops.gemm(q, k, out_fp32=True)                      # [HW, HW] fp32 scores
-            p = ops.softmax_rows(s, 1.0 / math.sqrt(c))
-            outs.append(ops.gemm(p, v_t))                          # [HW, C]
+            if tp != t:                                            # tiny feature maps only: zero-pad the tokens
+                tok = torch.zeros(tp, c, dtype=bf16, device=x.device)
+                tok[:t].copy_(n[i])
+            q, k = ops.gemm(tok, wq), ops.gemm(tok, wk)            # [T, C]
+            v_t = ops.gemm(wv, tok)                                # [C, T]  (V transposed: B operand of P @ V)
+            s = ops.gemm(q, k, out_fp32=True)                      # [T, T] fp32 scores
+            p = ops.softmax_rows(s, 1.0 / math.sqrt(c), valid_cols=t)
+            o_i = ops.gemm(p, v_t)                                 # [T, C]
+            outs.append(o_i if tp == t else o_i[:t].contiguous())
         o = outs[0].unsqueeze(0) if b == 1 else torch.stack(outs, 0)
         y = _linear(self, "out", self.out, o.reshape(b, h * w, c), residual=x.view(b, h * w, c))
         return y.view(b, h, w, c)

@@ -78,7 +78,7 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
                     float control_scale, float* workspace, cudaStream_t stream);
 int layer_norm(const void* x, void* y, const float* weight, const float* bias, int M, int C, float eps,
                cudaStream_t stream);
-int softmax_rows(const float* x, void* y, int rows, int cols, float scale, cudaStream_t stream);
+int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream);
 int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
                   long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
                   cudaStream_t stream);
@@ -170,9 +170,10 @@ int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* 
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;
   return layer_norm(x, y, weight, bias, M, C, eps, S(stream));
 }
-int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, float scale, void* stream) {
+int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t valid_cols, float scale,
+                        void* stream) {
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;
-  return softmax_rows(x, y, rows, cols, scale, S(stream));
+  return softmax_rows(x, y, rows, cols, valid_cols, scale, S(stream));
 }
 int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,

@@ -359,7 +359,8 @@ int layer_norm(const void* x, void* y, const float* weight, const float* bias, i
 // over an L2-resident row.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int rows, int cols, float scale) {
+softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int rows, int cols, int valid,
+                    float scale) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -367,20 +368,21 @@ softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, 
   if (row >= rows) return;
   const float* src = x + static_cast<size_t>(row) * cols;
   float mx = -INFINITY;
-  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, src[c]);
+  for (int c = lane; c < valid; c += 32) mx = fmaxf(mx, src[c]);
   mx = warp_max(mx) * scale;
   float sum = 0.f;
-  for (int c = lane; c < cols; c += 32) sum += __expf(src[c] * scale - mx);
+  for (int c = lane; c < valid; c += 32) sum += __expf(src[c] * scale - mx);
   const float inv = 1.0f / warp_sum(sum);
   __nv_bfloat16* dst = y + static_cast<size_t>(row) * cols;
-  for (int c = lane; c < cols; c += 32) dst[c] = __float2bfloat16(__expf(src[c] * scale - mx) * inv);
+  for (int c = lane; c < cols; c += 32)
+    dst[c] = __float2bfloat16(c < valid ? __expf(src[c] * scale - mx) * inv : 0.f);  // padded keys get weight 0
 }
 
-int softmax_rows(const float* x, void* y, int rows, int cols, float scale, cudaStream_t stream) {
-  if (rows <= 0 || cols <= 0) return B200SR_EINVAL;
+int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || valid <= 0 || valid > cols) return B200SR_EINVAL;
   const int grid = (rows + 7) / 8;
   return launch_k(softmax_rows_kernel, dim3(grid), dim3(256), 0, stream, 1, x, reinterpret_cast<__nv_bfloat16*>(y), rows,
-                  cols, scale) == cudaSuccess
+                  cols, valid, scale) == cudaSuccess
              ? B200SR_OK
              : B200SR_ELAUNCH;
 }

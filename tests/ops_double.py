@@ -106,8 +106,11 @@ def attention(q, k, v, heads, *, q_col=0, k_col=0, v_col=0, scale=None):
     return (att @ vf).transpose(1, 2).reshape(b, nq, c).to(bf16)
 
 
-def softmax_rows(x, scale=1.0):
-    return torch.softmax(x.float() * scale, dim=-1).to(bf16)
+def softmax_rows(x, scale=1.0, valid_cols=None):
+    v = x.shape[-1] if valid_cols is None else valid_cols
+    y = torch.zeros_like(x, dtype=torch.float32)
+    y[..., :v] = torch.softmax(x.float()[..., :v] * scale, dim=-1)
+    return y.to(bf16)
 
 
 def nchw_to_nhwc_bf16(x, scale=1.0):
