@@ -159,6 +159,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_epi = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);  // [4 warps][256] staged bias
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -325,8 +326,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ================================ epilogue (4 warps) ================================
+    // Per tile: the tile's bias slice is staged in (warp-private) shared memory and the first residual
+    // chunk is requested BEFORE waiting for the accumulator, so both overlap the mainloop; inside the
+    // chunk loop the TMEM load and the residual load of chunk c+1 are in flight while chunk c is
+    // processed and stored.
     const int sub = warp & 3;           // TMEM sub-partition this warp may access
     const int r = sub * 32 + lane;      // accumulator row == TMEM lane
+    float* s_bias = s_epi + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = work0; work < num_work; work += work_stride) {
@@ -352,22 +358,49 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         row = (static_cast<long long>(n) * p.OH + oh) * p.OW + ow;
         group = n;
       }
+      // stage bias[n0 .. n0+BN) (zero beyond N) — constant data, independent of earlier kernels
+      __syncwarp();
+      for (int j = lane; j < p.BN; j += 32)
+        s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      __syncwarp();
+      const bool has_res = p.residual != nullptr && valid;
+      const __nv_bfloat16* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
+      const float* rv_row = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.N + n0 : nullptr;
+      uint4 res_cur[4], res_nxt[4];
+      if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
+      if (has_res) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STAGE_COLS;
+      uint32_t a_cur[32], a_nxt[32];
+      tmem_ld32(t_row, a_cur);
       for (int c = 0; c < p.BN; c += 32) {
-        uint32_t a[32];
-        tmem_ld32(t_row + c, a);
         tmem_ld_wait();
+        const bool more = c + 32 < p.BN;
+        if (more) {
+          tmem_ld32(t_row + c + 32, a_nxt);
+          if (has_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              res_nxt[q] = (n0 + c + 32 + q * 8 < p.N)
+                               ? __ldg(reinterpret_cast<const uint4*>(res_row + c + 32) + q)
+                               : make_uint4(0, 0, 0, 0);
+          }
+        }
         const int col0 = n0 + c;
         if (valid && col0 < p.N) {
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + j);
+            v[j] = __uint_as_float(a_cur[j]) + b4.x;
+            v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
           }
           if (p.geglu) {
             // columns [0,16) = value, [16,32) = gate of the same 16 output features
@@ -392,29 +425,31 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
             }
-            if (p.rowvec != nullptr) {
-              const float* rv = p.rowvec + static_cast<long long>(group) * p.N + col0;
+            if (rv_row != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] += __ldg(rv + j);
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.N) {
+                  const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv_row + c + j));
+                  v[j] += r4.x;
+                  v[j + 1] += r4.y;
+                  v[j + 2] += r4.z;
+                  v[j + 3] += r4.w;
+                }
+              }
             }
-            if (p.residual != nullptr) {
-              const __nv_bfloat16* res = p.residual + row * p.ldr + col0;
+            if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (col0 + q * 8 < p.N) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(res) + q);
-                  const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
-                               f3 = unpack_bf16x2(u.w);
-                  v[q * 8 + 0] += f0.x;
-                  v[q * 8 + 1] += f0.y;
-                  v[q * 8 + 2] += f1.x;
-                  v[q * 8 + 3] += f1.y;
-                  v[q * 8 + 4] += f2.x;
-                  v[q * 8 + 5] += f2.y;
-                  v[q * 8 + 6] += f3.x;
-                  v[q * 8 + 7] += f3.y;
-                }
+                const float2 f0 = unpack_bf16x2(res_cur[q].x), f1 = unpack_bf16x2(res_cur[q].y),
+                             f2 = unpack_bf16x2(res_cur[q].z), f3 = unpack_bf16x2(res_cur[q].w);
+                v[q * 8 + 0] += f0.x;
+                v[q * 8 + 1] += f0.y;
+                v[q * 8 + 2] += f1.x;
+                v[q * 8 + 3] += f1.y;
+                v[q * 8 + 4] += f2.x;
+                v[q * 8 + 5] += f2.y;
+                v[q * 8 + 6] += f3.x;
+                v[q * 8 + 7] += f3.y;
               }
             }
             if (p.act == 1) {
@@ -443,6 +478,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+        }
+        if (more) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a_cur[j] = a_nxt[j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) res_cur[q] = res_nxt[q];
         }
       }
       // release this accumulator stage back to the MMA warp
@@ -509,14 +550,14 @@ static int pick_bn(int m_blocks, int N, int k_iters, int sms, int cluster) {
 
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - 4096 /*epilogue bias staging*/;
   const int stage_bytes = A_STAGE_BYTES + (p.BN / kCluster) * BLOCK_K * 2;
   int stages = smem_budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.k_iters + 1) stages = p.k_iters + 1;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + 4096;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=

@@ -1,0 +1,116 @@
+"""Per-op in-graph timing: each op is captured REP times into one CUDA graph (cycling through enough
+distinct weight tensors to keep them cold in L2, like the real step) and the replay is timed.
+This is the steady-state cost of one launch inside the step graph (PDL edges included)."""
+import math, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "remote-sensing-vision-language-diffusion-model_b200"))
+import torch
+from b200sr import ops
+bf16 = torch.bfloat16
+dev = "cuda"
+REP = 48
+def r(*s, scale=0.5): return (torch.randn(*s, device=dev) * scale).to(bf16)
+
+def graph_time(make_calls):
+    """make_calls(i) enqueues the i-th launch."""
+    for i in range(REP): make_calls(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(REP): make_calls(i)
+    for _ in range(2): g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 5 / REP * 1e3  # us per launch
+
+rows = []
+def gemm_case(M, N, K, geglu=False, residual=False, n_in_step=0):
+    nw = max(2, min(REP, int(160e6 / (N * K * 2)) + 1))
+    ws = [r(N, K, scale=0.03) for _ in range(nw)]
+    bs = torch.randn(N, device=dev)
+    a = r(M, K); res = r(M, N) if residual else None
+    out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=bf16)
+    t = graph_time(lambda i: ops.gemm(a, ws[i % nw], bs, residual=res, geglu=geglu, out=out))
+    fl = 2.0 * M * N * K
+    rows.append((f"gemm M{M} N{N} K{K}{' geglu' if geglu else ''}", t, fl / t / 1e6, n_in_step))
+def conv_case(N, H, W, Cin, Cout, n_in_step=0):
+    nw = max(2, min(REP, int(160e6 / (Cout * 9 * Cin * 2)) + 1))
+    ws = [r(Cout, 9 * Cin, scale=0.02) for _ in range(nw)]
+    x = r(N, H, W, Cin); b = torch.randn(Cout, device=dev); emb = torch.randn(N, Cout, device=dev)
+    t = graph_time(lambda i: ops.conv3x3(x, ws[i % nw], b, rowvec=emb))
+    fl = 2.0 * N * H * W * Cout * 9 * Cin
+    rows.append((f"conv {N}x{H}x{W} {Cin}->{Cout}", t, fl / t / 1e6, n_in_step))
+def attn_case(B, H, Nq, Nk, n_in_step=0):
+    C = H * 64
+    if Nq == Nk:
+        qkv = r(B, Nq, 3 * C)
+        t = graph_time(lambda i: ops.attention(qkv, qkv, qkv, H, q_col=0, k_col=C, v_col=2 * C))
+    else:
+        q = r(B, Nq, C); kv = r(B, Nk, 2 * C)
+        t = graph_time(lambda i: ops.attention(q, kv, kv, H, q_col=0, k_col=0, v_col=C))
+    fl = 4.0 * B * H * Nq * Nk * 64
+    rows.append((f"attn B{B} H{H} Nq{Nq} Nk{Nk}", t, fl / t / 1e6, n_in_step))
+def ln_case(M, C, n_in_step=0):
+    x = r(M, C); g = torch.ones(C, device=dev); b = torch.zeros(C, device=dev)
+    t = graph_time(lambda i: ops.layer_norm(x, g, b))
+    rows.append((f"layer_norm M{M} C{C}", t, 4.0 * M * C / t / 1e6, n_in_step))   # "TF/s" column = TB/s here
+def gn_case(N, HW, C, n_in_step=0):
+    x = r(N, HW, C); g = torch.ones(C, device=dev); b = torch.zeros(C, device=dev)
+    t = graph_time(lambda i: ops.group_norm(x, g, b, silu=True))
+    rows.append((f"group_norm N{N} HW{HW} C{C} (2 kernels)", t, 6.0 * N * HW * C / t / 1e6, n_in_step))
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "gemm"):
+    gemm_case(2048, 10240, 1280, geglu=True, n_in_step=90)
+    gemm_case(2048, 1280, 1280, residual=True, n_in_step=293)
+    gemm_case(2048, 1280, 5120, residual=True, n_in_step=90)
+    gemm_case(2048, 3840, 1280, n_in_step=90)
+    gemm_case(8192, 5120, 640, geglu=True, n_in_step=14)
+    gemm_case(8192, 640, 640, residual=True, n_in_step=60)
+    gemm_case(8192, 640, 2560, residual=True, n_in_step=14)
+    gemm_case(8192, 1920, 640, n_in_step=14)
+    conv_case(2, 32, 32, 1280, 1280, 17)
+    conv_case(2, 128, 128, 320, 320, 11)
+    conv_case(2, 64, 64, 640, 640, 9)
+if which in ("all", "attn"):
+    attn_case(2, 20, 1024, 1024, 91)
+    attn_case(2, 10, 4096, 4096, 15)
+    attn_case(2, 20, 1024, 77, 90)
+    attn_case(2, 10, 4096, 77, 14)
+if which in ("all", "norm"):
+    ln_case(2048, 1280, 270); ln_case(8192, 640, 42)
+    gn_case(2, 1024, 1280, 28); gn_case(2, 16384, 320, 12); gn_case(2, 4096, 640, 17)
+tot = 0.0
+print(f"{'op':46s} {'us/launch':>9s} {'TF/s|TB/s':>9s} {'n/step':>6s} {'ms/step':>8s}")
+for name, t, rate, n in rows:
+    tot += t * n / 1e3
+    print(f"{name:46s} {t:9.1f} {rate:9.1f} {n:6d} {t * n / 1e3:8.3f}")
+print("sum ms/step of listed ops:", round(tot, 3))
+if which == "fixed":
+    rows.clear()
+    def g2(M, N, K, residual=False, bias=True, bn=0, label=""):
+        nw = max(2, min(REP, int(160e6 / (N * K * 2)) + 1))
+        ws = [r(N, K, scale=0.03) for _ in range(nw)]
+        bs = torch.randn(N, device=dev) if bias else None
+        a = r(M, K); res = r(M, N) if residual else None
+        out = torch.empty(M, N, device=dev, dtype=bf16)
+        t = graph_time(lambda i: ops.gemm(a, ws[i % nw], bs, residual=res, out=out, force_bn=bn))
+        rows.append((f"gemm M{M} N{N} K{K} res={int(residual)} bias={int(bias)} bn={bn} {label}", t, 2.0 * M * N * K / t / 1e6, 0))
+    for K in (64, 128, 256, 640, 1280, 2560):
+        g2(2048, 1280, K)
+    g2(2048, 1280, 1280, residual=True)
+    g2(2048, 1280, 1280, bias=False)
+    for bn in (96, 128, 160, 192, 256):
+        g2(2048, 1280, 1280, bn=bn)
+    g2(128, 1280, 1280, label="(1 m-block, cluster 1)")
+    g2(256, 1280, 1280, label="(1 pair)")
+    g2(2048, 160, 1280, label="(8 pairs only)")
+    x = r(2048, 1280)
+    t = graph_time(lambda i: ops.silu(x))
+    rows.append(("silu 2048x1280 (trivial elementwise kernel)", t, 0.0, 0))
+    print(f"{'op':70s} {'us/launch':>9s} {'TF/s':>8s}")
+    for name, t, rate, n in rows:
+        print(f"{name:70s} {t:9.1f} {rate:8.1f}")
