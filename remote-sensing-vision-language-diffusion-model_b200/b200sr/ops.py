@@ -75,10 +75,26 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 
 _ws_cache: dict = {}
+_ws_slot = [0]  # scratch buffers are per (device, slot): work issued concurrently on a second stream uses slot 1
+
+
+class workspace_slot:
+    """Context manager selecting the scratch-buffer slot for ops enqueued inside it (one per concurrent stream)."""
+
+    def __init__(self, slot: int):
+        self.slot = slot
+
+    def __enter__(self):
+        self.prev = _ws_slot[0]
+        _ws_slot[0] = self.slot
+
+    def __exit__(self, *exc):
+        _ws_slot[0] = self.prev
+        return False
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.type, device.index)
+    key = (device.type, device.index, _ws_slot[0])
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() * 4 < nbytes:
         if torch.cuda.is_current_stream_capturing() and ws is not None:
@@ -470,7 +486,7 @@ def rel_l1_similarity(prev: torch.Tensor, cur: torch.Tensor, threshold: torch.Te
     """Returns a device fp32[2]: (diff, diff < threshold) — DFBCache.are_two_tensors_similar."""
     _req(prev, bf16, "rel_l1.prev")
     _req(cur, bf16, "rel_l1.cur")
-    key = (prev.device.type, prev.device.index)
+    key = (prev.device.type, prev.device.index, _ws_slot[0])
     ws = _rel_ws.get(key)
     if ws is None:
         ws = torch.zeros(2, dtype=torch.float64, device=prev.device)

@@ -26,6 +26,11 @@ import torch
 
 from . import ops
 
+
+def ops_to_nhwc(x_nchw_view: torch.Tensor) -> torch.Tensor:
+    return x_nchw_view.permute(0, 2, 3, 1)
+
+
 SIGMA_MAX = 14.6146
 
 
@@ -112,9 +117,13 @@ class Stage2Engine:
     """
 
     def __init__(self, wrapper, num_steps=50, s_churn=5.0, s_noise=1.003, cfg_scale=4.0, cfg_scale_min=7.5,
-                 control_scale=1.0, use_graphs=True, device="cuda", hoist_text_kv=True):
+                 control_scale=1.0, use_graphs=True, device="cuda", hoist_text_kv=True, dual_stream=True):
         self.wrapper = wrapper
         self.hoist_text_kv = hoist_text_kv
+        # drive the two networks directly (and concurrently) when the wrapper is our own ControlWrapper
+        self._direct = hasattr(wrapper, "control_model") and hasattr(getattr(wrapper, "diffusion_model", None), "_input_stage")
+        self.dual_stream = dual_stream and self._direct and torch.device(device).type == "cuda"
+        self._side = None
         self.sched = StepSchedule(num_steps, s_churn, 0.0, float("inf"), s_noise, cfg_scale, cfg_scale_min)
         self.control_scale = control_scale
         self.use_graphs = use_graphs
@@ -178,17 +187,54 @@ class Stage2Engine:
         st["t"].fill_(0).add_(self._idx_dev[i])
         return st
 
+    def _net_first_half(self, net_in):
+        """Control net and UNet input blocks are independent given (x, t, cond): the control net runs on a
+        second stream (forked / joined with events, captured into the same graph), so its launch-latency and
+        tail bubbles overlap the UNet encoder's kernels.  Returns (control, h, hs, emb, ctx) as NHWC tensors."""
+        st, w, c = self._static, self.wrapper, self.cond
+        x_nchw = net_in.permute(0, 3, 1, 2)
+        if not self.dual_stream:
+            control = w.control_model.forward_nhwc(ops_to_nhwc(c["control"]), st["t"], net_in, c["crossattn"], c["vector"])
+        unet = w.diffusion_model
+        main = torch.cuda.current_stream()
+        if self.dual_stream:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side), ops.workspace_slot(1):
+                control = w.control_model.forward_nhwc(ops_to_nhwc(c["control"]), st["t"], net_in, c["crossattn"],
+                                                       c["vector"])
+        emb = unet._embed(st["t"], c["vector"])
+        h, hs = unet._input_stage(net_in, emb, c["crossattn"])
+        if self.dual_stream:
+            main.wait_stream(self._side)
+            if not torch.cuda.is_current_stream_capturing():
+                for t_ in control:
+                    t_.record_stream(main)
+        del x_nchw
+        return control, h, hs, emb
+
     def _body_full(self):
         st = self._static
         x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
-        eps = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "none", None)
+        if self._direct:
+            control, h, hs, emb = self._net_first_half(net_in)
+            eps = self.wrapper.diffusion_model._output_stage(h, hs, emb, self.cond["crossattn"], control, self.control_scale)
+        else:
+            eps = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "none", None)
         x_next, den = ops.sampler_post(eps, x_hat, st["sc"], True, True)
         st["x_next"], st["den"] = x_next, den
 
     def _body_stage1(self):
         st = self._static
         x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
-        info = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "input_stage1", None)
+        if self._direct:
+            control, h, hs, emb = self._net_first_half(net_in)
+            info = {"mode": "input", "h": h.permute(0, 3, 1, 2), "hs": [t.permute(0, 3, 1, 2) for t in hs], "emb": emb,
+                    "context": self.cond["crossattn"], "control": [t.permute(0, 3, 1, 2) for t in control],
+                    "adapter_idx": len(self.wrapper.diffusion_model.project_modules) - 1, "control_idx": len(control) - 1}
+        else:
+            info = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "input_stage1", None)
         st["x_hat"], st["info"] = x_hat, info
         h = info["h"].permute(0, 2, 3, 1)
         if "prev_h" not in st:
