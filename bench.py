@@ -144,7 +144,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     wrapper = wrapper.to(dev)
     x0, c, uc = inputs.stage2_inputs(latent=LATENT, seed=1234 + rank)
     eng = Stage2Engine(wrapper, use_graphs=not args.no_graphs, device=dev)
-    eng.set_condition({k: v.to(dev) for k, v in c.items()}, {k: v.to(dev) for k, v in uc.items()})
+    c_dev, uc_dev = {k: v.to(dev) for k, v in c.items()}, {k: v.to(dev) for k, v in uc.items()}
+    eng.set_condition(c_dev, uc_dev)
     g = torch.Generator(device="cpu").manual_seed(99 + rank)
     noise_host = torch.randn(x0.shape, generator=g).pin_memory()
     x_host = x0.clone().pin_memory()
@@ -196,8 +197,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         return
 
     # ---- dominant-kernel roofline: per-launch CUDA-event timing of the tcgen05 GEMM/conv kernel -----
-    eager = Stage2Engine(wrapper, use_graphs=False, device=dev)
-    eager.cond = eng.cond
+    # single-stream eager pass so that per-launch event pairs do not overlap
+    eager = Stage2Engine(wrapper, use_graphs=False, device=dev, dual_stream=False, split_cfg=False)
+    eager.set_condition(c_dev, uc_dev)
     eager.step(x, step_i, noise, 0.0)
     recs = []
     torch.cuda.synchronize()

@@ -264,8 +264,9 @@ class CrossAttention(nn.Module, Packed):
             qkv = ops.gemm(x, w)
             return ops.attention(qkv, qkv, qkv, self.heads, q_col=0, k_col=inner, v_col=2 * inner, scale=self.scale)
         q = _linear(self, "q", self.to_q, x)
-        if context is self.__dict__.get("_static_ctx"):
-            kv = self._static_kv  # hoisted by bind_static_context(): the text context is constant over the steps
+        bound = self.__dict__.get("_static", {}).get(id(context))
+        if bound is not None and bound[0] is context:
+            kv = bound[1]  # hoisted by bind_static_context(): the text context is constant over the steps
         else:
             kv = ops.gemm(context, self._wkv())
         return ops.attention(q, kv, kv, self.heads, q_col=0, k_col=0, v_col=inner, scale=self.scale)
@@ -276,17 +277,17 @@ class CrossAttention(nn.Module, Packed):
     def bind_static_context(self, context: Optional[torch.Tensor]) -> None:
         """Precompute K/V of a context that stays constant across sampler steps (the text embedding:
         SURVEY.md 8(a) a8 notes the reference re-projects it every step).  `context` must be the very
-        tensor object later passed to forward(); results are written in place when the buffer exists
-        so captured CUDA graphs stay valid.  Pass None to unbind."""
+        tensor object later passed to forward(); several contexts may be bound (one per CFG half).
+        Results are written in place when a buffer for that object exists, so captured CUDA graphs stay
+        valid.  Pass None to unbind everything."""
+        table = self.__dict__.setdefault("_static", {})
         if context is None:
-            self.__dict__.pop("_static_ctx", None)
-            self.__dict__.pop("_static_kv", None)
+            table.clear()
             return
-        old = self.__dict__.get("_static_kv")
+        old = table.get(id(context))
         shape = (*context.shape[:-1], 2 * self.to_q.weight.shape[0])
-        out = old if (old is not None and tuple(old.shape) == shape and old.device == context.device) else None
-        self._static_kv = ops.gemm(context, self._wkv(), out=out)
-        self._static_ctx = context
+        out = old[1] if (old is not None and old[0] is context and tuple(old[1].shape) == shape) else None
+        table[id(context)] = (context, ops.gemm(context, self._wkv(), out=out))
 
     def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
                 residual: Optional[torch.Tensor] = None, alpha: float = 1.0):

@@ -117,13 +117,16 @@ class Stage2Engine:
     """
 
     def __init__(self, wrapper, num_steps=50, s_churn=5.0, s_noise=1.003, cfg_scale=4.0, cfg_scale_min=7.5,
-                 control_scale=1.0, use_graphs=True, device="cuda", hoist_text_kv=True, dual_stream=True):
+                 control_scale=1.0, use_graphs=True, device="cuda", hoist_text_kv=True, dual_stream=True, split_cfg=False):
         self.wrapper = wrapper
         self.hoist_text_kv = hoist_text_kv
         # drive the two networks directly (and concurrently) when the wrapper is our own ControlWrapper
         self._direct = hasattr(wrapper, "control_model") and hasattr(getattr(wrapper, "diffusion_model", None), "_input_stage")
         self.dual_stream = dual_stream and self._direct and torch.device(device).type == "cuda"
+        # run the two CFG halves (independent through the whole network) as two concurrent stream pairs
+        self.split_cfg = split_cfg and self.dual_stream
         self._side = None
+        self._streams = None
         self.sched = StepSchedule(num_steps, s_churn, 0.0, float("inf"), s_noise, cfg_scale, cfg_scale_min)
         self.control_scale = control_scale
         self.use_graphs = use_graphs
@@ -142,6 +145,7 @@ class Stage2Engine:
     def set_condition(self, c: Dict[str, torch.Tensor], uc: Dict[str, torch.Tensor]) -> None:
         """guiders.py:65-74: batch = [uncond ; cond]; casts once to bf16 (context / vector / control)."""
         cat = lambda k: torch.cat((uc[k], c[k]), 0).to(self.device).float().contiguous()  # noqa: E731
+        self.half_b = c["crossattn"].shape[0]
         new = {"crossattn": ops.cast_bf16(cat("crossattn")), "vector": ops.cast_bf16(cat("vector")),
                "control": ops.nchw_to_nhwc_bf16(cat("control")).permute(0, 3, 1, 2)}
         if self.cond is not None and all(self.cond[k].shape == new[k].shape for k in new):
@@ -150,10 +154,19 @@ class Stage2Engine:
         else:
             self.cond = new
             self._graphs.clear()
+        # per-CFG-half views for the split-batch schedule: slices of the same storage, created once per
+        # conditioning buffer so their identity (K/V binding, captured graphs) stays stable
+        if self.split_cfg and getattr(self, "_cond_half_of", None) is not self.cond:
+            hb = self.half_b
+            self.cond_half = [{k: v[i:i + hb] for k, v in self.cond.items()} for i in range(0, 2 * hb, hb)]
+            self._cond_half_of = self.cond
         if self.hoist_text_kv and hasattr(self.wrapper, "modules"):
             from .modules import bind_text_context
 
             bind_text_context(self.wrapper, self.cond["crossattn"])
+            if self.split_cfg:
+                for ch in self.cond_half:
+                    bind_text_context(self.wrapper, ch["crossattn"])
         self.reset_cache()
 
     def reset_cache(self):
@@ -214,10 +227,47 @@ class Stage2Engine:
         del x_nchw
         return control, h, hs, emb
 
+    def _net_split(self, net_in):
+        """Whole network with the two CFG halves on two stream pairs (each: UNet + its control net)."""
+        st, w = self._static, self.wrapper
+        unet = w.diffusion_model
+        main = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream() for _ in range(4)]
+        outs = []
+        hb = self.half_b
+        for k in range(2):
+            s_net, s_ctl = self._streams[2 * k], self._streams[2 * k + 1]
+            ck = self.cond_half[k]
+            xin = net_in[k * hb:(k + 1) * hb]
+            tk = st["t"][k * hb:(k + 1) * hb]
+            s_net.wait_stream(main)
+            with torch.cuda.stream(s_net):
+                s_ctl.wait_stream(s_net)
+                with torch.cuda.stream(s_ctl), ops.workspace_slot(2 * k + 1):
+                    control = w.control_model.forward_nhwc(ops_to_nhwc(ck["control"]), tk, xin, ck["crossattn"],
+                                                           ck["vector"])
+                with ops.workspace_slot(2 * k + 2):
+                    emb = unet._embed(tk, ck["vector"])
+                    h, hs = unet._input_stage(xin, emb, ck["crossattn"])
+                    s_net.wait_stream(s_ctl)
+                    if not torch.cuda.is_current_stream_capturing():
+                        for t_ in control:
+                            t_.record_stream(s_net)
+                    outs.append(unet._output_stage(h, hs, emb, ck["crossattn"], control, self.control_scale))
+        for k in range(2):
+            main.wait_stream(self._streams[2 * k])
+        if not torch.cuda.is_current_stream_capturing():
+            for o in outs:
+                o.record_stream(main)
+        return torch.cat(outs, 0)
+
     def _body_full(self):
         st = self._static
         x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
-        if self._direct:
+        if self.split_cfg:
+            eps = self._net_split(net_in)
+        elif self._direct:
             control, h, hs, emb = self._net_first_half(net_in)
             eps = self.wrapper.diffusion_model._output_stage(h, hs, emb, self.cond["crossattn"], control, self.control_scale)
         else:
