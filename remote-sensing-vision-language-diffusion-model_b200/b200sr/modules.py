@@ -255,8 +255,8 @@ class CrossAttention(nn.Module, Packed):
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
         self.backend = backend
 
-    def attend(self, x, context=None):
-        """x: [B, T, C] bf16 -> attention output before to_out, [B, T, inner]."""
+    def attend(self, x, context=None, kv=None):
+        """x: [B, T, C] bf16 -> attention output before to_out, [B, T, inner].  `kv`: precomputed [B, Tk, 2*inner]."""
         inner = self.to_q.weight.shape[0]
         if context is None:
             w = self._pk("qkv", (self.to_q.weight, self.to_k.weight, self.to_v.weight),
@@ -265,7 +265,9 @@ class CrossAttention(nn.Module, Packed):
             return ops.attention(qkv, qkv, qkv, self.heads, q_col=0, k_col=inner, v_col=2 * inner, scale=self.scale)
         q = _linear(self, "q", self.to_q, x)
         bound = self.__dict__.get("_static", {}).get(id(context))
-        if bound is not None and bound[0] is context:
+        if kv is not None:
+            pass
+        elif bound is not None and bound[0] is context:
             kv = bound[1]  # hoisted by bind_static_context(): the text context is constant over the steps
         else:
             kv = ops.gemm(context, self._wkv())
@@ -290,12 +292,12 @@ class CrossAttention(nn.Module, Packed):
         table[id(context)] = (context, ops.gemm(context, self._wkv(), out=out))
 
     def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
-                residual: Optional[torch.Tensor] = None, alpha: float = 1.0):
+                residual: Optional[torch.Tensor] = None, alpha: float = 1.0, kv: Optional[torch.Tensor] = None):
         if mask is not None or additional_tokens is not None or n_times_crossframe_attn_in_self:
             raise NotImplementedError("masks / additional tokens / cross-frame attention are not on the hot path")
         x = tokens_bf16(x)
         ctx = tokens_bf16(context) if context is not None else None
-        return _linear(self, "out", self.to_out[0], self.attend(x, ctx), residual=residual, alpha=alpha)
+        return _linear(self, "out", self.to_out[0], self.attend(x, ctx, kv), residual=residual, alpha=alpha)
 
 
 MemoryEfficientCrossAttention = CrossAttention  # attention.py:288-373 computes the same function
@@ -558,17 +560,28 @@ class ZeroSFT(nn.Module, Packed):
         self.pre_concat = bool(concat_channels != 0)
         self.mask = mask
 
-    def forward_nhwc(self, c, h, h_ori=None, control_scale=1):
+    def precompute(self, c):
+        """Everything that depends only on the control feature c (zero_conv(c), gamma, beta): can run on another
+        stream while the UNet is still producing h."""
+        actv = _conv3x3(self, "mlp", self.mlp_shared[0], c, act=1)
+        return {"zc": _linear(self, "zero_conv", self.zero_conv, c),
+                "gamma": _conv3x3(self, "mul", self.zero_mul, actv), "beta": _conv3x3(self, "add", self.zero_add, actv)}
+
+    def forward_nhwc(self, c, h, h_ori=None, control_scale=1, pre=None):
         assert self.mask is False
         cat = h_ori is not None and self.pre_concat
         if h_ori is not None and not self.pre_concat:
             raise NotImplementedError("post-concat ZeroSFT is not used by LightGLVUNet")
         control_scale = float(control_scale)
-        hz = _linear(self, "zero_conv", self.zero_conv, c, residual=h)  # h + zero_conv(c)
-        hc = ops.concat_add(h_ori, hz) if cat else hz
-        actv = _conv3x3(self, "mlp", self.mlp_shared[0], c, act=1)
-        gamma = _conv3x3(self, "mul", self.zero_mul, actv)
-        beta = _conv3x3(self, "add", self.zero_add, actv)
+        if pre is None:
+            hz = _linear(self, "zero_conv", self.zero_conv, c, residual=h)  # h + zero_conv(c)
+            hc = ops.concat_add(h_ori, hz) if cat else hz
+            actv = _conv3x3(self, "mlp", self.mlp_shared[0], c, act=1)
+            gamma = _conv3x3(self, "mul", self.zero_mul, actv)
+            beta = _conv3x3(self, "add", self.zero_add, actv)
+        else:
+            hc = ops.concat_add(h_ori, h, pre["zc"]) if cat else ops.axpy(h, pre["zc"], 1.0)
+            gamma, beta = pre["gamma"], pre["beta"]
         raw = None
         if control_scale != 1.0:
             raw = ops.concat_add(h_ori, h) if cat else h
@@ -589,12 +602,21 @@ class ZeroCrossAttn(nn.Module, Packed):
         self.norm2 = normalization(context_dim)
         self.mask = mask
 
-    def forward_nhwc(self, context, x, control_scale=1):
+    def precompute(self, context):
+        """GN(context) tokens -> K/V projection: depends only on the control feature."""
+        b, h, w, cc = context.shape
+        ct = _gn(self.norm2, context).view(b, h * w, cc)
+        return {"kv": ops.gemm(ct, self.attn._wkv())}
+
+    def forward_nhwc(self, context, x, control_scale=1, pre=None):
         assert self.mask is False
         b, h, w, c = x.shape
         xt = _gn(self.norm1, x).view(b, h * w, c)
-        ct = _gn(self.norm2, context).view(b, h * w, context.shape[-1])
-        out = self.attn(xt, ct, residual=x.view(b, h * w, c), alpha=float(control_scale))
+        if pre is None:
+            ct = _gn(self.norm2, context).view(b, h * w, context.shape[-1])
+            out = self.attn(xt, ct, residual=x.view(b, h * w, c), alpha=float(control_scale))
+        else:
+            out = self.attn(xt, xt, residual=x.view(b, h * w, c), alpha=float(control_scale), kv=pre["kv"])
         return out.view(b, h, w, c)
 
     def forward(self, context, x, control_scale=1):
@@ -682,23 +704,51 @@ class LightGLVUNet(UNetModel):
             hs.append(h)
         return h, hs
 
-    def _output_stage(self, h, hs, emb, context, control, control_scale):
+    def _adapter_controls(self, n_control: int):
+        """adapter index -> control index, in the order forward() consumes them (SR_modules.py:628-655)."""
+        plan = {}
+        a, ci = len(self.project_modules) - 1, n_control - 1
+        plan[a] = ci
+        a -= 1
+        ci -= 1
+        for module in self.output_blocks:
+            plan[a] = ci
+            a -= 1
+            if len(module) == 3:
+                plan[a] = ci
+                a -= 1
+            ci -= 1
+        return plan
+
+    def precompute_adapters(self, control):
+        """Adapter work that needs only the control features (runs on the control stream in the engine)."""
+        return {a: self.project_modules[a].precompute(control[ci]) for a, ci in self._adapter_controls(len(control)).items()}
+
+    def _middle(self, h, emb, context):
+        return self.middle_block.forward_nhwc(h, emb, context)
+
+    def _output_stage(self, h, hs, emb, context, control, control_scale, pre=None, middle_done=False):
         hs = list(hs)
+        pre = pre or {}
         adapter_idx = len(self.project_modules) - 1
         control_idx = len(control) - 1
-        h = self.middle_block.forward_nhwc(h, emb, context)
-        h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], h, control_scale=control_scale)
+        if not middle_done:
+            h = self.middle_block.forward_nhwc(h, emb, context)
+        h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], h, control_scale=control_scale,
+                                                           pre=pre.get(adapter_idx))
         adapter_idx -= 1
         control_idx -= 1
         for module in self.output_blocks:
             _h = hs.pop()
-            h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], _h, h, control_scale=control_scale)
+            h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], _h, h, control_scale=control_scale,
+                                                               pre=pre.get(adapter_idx))
             adapter_idx -= 1
             if len(module) == 3:
                 assert isinstance(module[2], Upsample)
                 h = module[0].forward_nhwc(h, emb)
                 h = module[1].forward_nhwc(h, context)
-                h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], h, control_scale=control_scale)
+                h = self.project_modules[adapter_idx].forward_nhwc(control[control_idx], h, control_scale=control_scale,
+                                                                   pre=pre.get(adapter_idx))
                 adapter_idx -= 1
                 h = module[2].forward_nhwc(h)
             else:

@@ -200,32 +200,40 @@ class Stage2Engine:
         st["t"].fill_(0).add_(self._idx_dev[i])
         return st
 
-    def _net_first_half(self, net_in):
-        """Control net and UNet input blocks are independent given (x, t, cond): the control net runs on a
-        second stream (forked / joined with events, captured into the same graph), so its launch-latency and
-        tail bubbles overlap the UNet encoder's kernels.  Returns (control, h, hs, emb, ctx) as NHWC tensors."""
+    def _net_first_half(self, net_in, with_middle=False):
+        """Control net and UNet encoder are independent given (x, t, cond): the control net (followed by the
+        adapter work that only needs control features: ZeroSFT gamma / beta / zero_conv, ZeroCrossAttn K/V) runs
+        on a second stream, forked / joined with events and captured into the same graph, so its launch-latency
+        and tail bubbles overlap the UNet encoder (and, with_middle, the middle block).
+        Returns (control, h, hs, emb, pre)."""
         st, w, c = self._static, self.wrapper, self.cond
-        x_nchw = net_in.permute(0, 3, 1, 2)
-        if not self.dual_stream:
-            control = w.control_model.forward_nhwc(ops_to_nhwc(c["control"]), st["t"], net_in, c["crossattn"], c["vector"])
         unet = w.diffusion_model
+        lq = ops_to_nhwc(c["control"])
+        pre = None
+        if not self.dual_stream:
+            control = w.control_model.forward_nhwc(lq, st["t"], net_in, c["crossattn"], c["vector"])
+            emb = unet._embed(st["t"], c["vector"])
+            h, hs = unet._input_stage(net_in, emb, c["crossattn"])
+            if with_middle:
+                h = unet._middle(h, emb, c["crossattn"])
+            return control, h, hs, emb, pre
         main = torch.cuda.current_stream()
-        if self.dual_stream:
-            if self._side is None:
-                self._side = torch.cuda.Stream()
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side), ops.workspace_slot(1):
-                control = w.control_model.forward_nhwc(ops_to_nhwc(c["control"]), st["t"], net_in, c["crossattn"],
-                                                       c["vector"])
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side), ops.workspace_slot(1):
+            control = w.control_model.forward_nhwc(lq, st["t"], net_in, c["crossattn"], c["vector"])
+            if with_middle:
+                pre = unet.precompute_adapters(control)
         emb = unet._embed(st["t"], c["vector"])
         h, hs = unet._input_stage(net_in, emb, c["crossattn"])
-        if self.dual_stream:
-            main.wait_stream(self._side)
-            if not torch.cuda.is_current_stream_capturing():
-                for t_ in control:
-                    t_.record_stream(main)
-        del x_nchw
-        return control, h, hs, emb
+        if with_middle:
+            h = unet._middle(h, emb, c["crossattn"])
+        main.wait_stream(self._side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t_ in list(control) + ([v for d in pre.values() for v in d.values()] if pre else []):
+                t_.record_stream(main)
+        return control, h, hs, emb, pre
 
     def _net_split(self, net_in):
         """Whole network with the two CFG halves on two stream pairs (each: UNet + its control net)."""
@@ -268,8 +276,9 @@ class Stage2Engine:
         if self.split_cfg:
             eps = self._net_split(net_in)
         elif self._direct:
-            control, h, hs, emb = self._net_first_half(net_in)
-            eps = self.wrapper.diffusion_model._output_stage(h, hs, emb, self.cond["crossattn"], control, self.control_scale)
+            control, h, hs, emb, pre = self._net_first_half(net_in, with_middle=True)
+            eps = self.wrapper.diffusion_model._output_stage(h, hs, emb, self.cond["crossattn"], control,
+                                                             self.control_scale, pre=pre, middle_done=True)
         else:
             eps = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self.cond, self.control_scale, "none", None)
         x_next, den = ops.sampler_post(eps, x_hat, st["sc"], True, True)
@@ -279,7 +288,7 @@ class Stage2Engine:
         st = self._static
         x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
         if self._direct:
-            control, h, hs, emb = self._net_first_half(net_in)
+            control, h, hs, emb, _ = self._net_first_half(net_in)
             info = {"mode": "input", "h": h.permute(0, 3, 1, 2), "hs": [t.permute(0, 3, 1, 2) for t in hs], "emb": emb,
                     "context": self.cond["crossattn"], "control": [t.permute(0, 3, 1, 2) for t in control],
                     "adapter_idx": len(self.wrapper.diffusion_model.project_modules) - 1, "control_idx": len(control) - 1}
