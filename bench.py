@@ -221,9 +221,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dense_fl, dense_ms, dense_n = (sum(d[i] for d in dense) for i in range(3))
     achieved = dense_fl / (dense_ms * 1e-3) / 1e12 if dense_ms else 0.0
     peak = pk["bf16_tflops_sustained"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "achieved": achieved, "peak": peak, "peak_source": f"{pk_src} bf16_tflops_sustained", "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "launches_per_step": dense_n,
+                "frac": achieved / peak, "traffic": traffic, "launches_per_step": dense_n,
                 "avg_launch_us": 1e3 * dense_ms / max(dense_n, 1),
                 "share_of_step_time": dense_ms / sum(v[1] for v in agg.values()) if agg else None,
                 "by_kind": {k: {"tflop": v[0] / 1e12, "ms": v[1], "launches": v[2],
