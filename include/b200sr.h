@@ -77,7 +77,9 @@ int b200sr_conv3x3_small(const void* x, const void* w, const float* bias, const 
 /* GroupNorm over NHWC bf16 with optional fused SiLU and ZeroSFT modulation:
  *   y = GN(x) * w + b ; [SiLU] ; [y = y * (1 + gamma) + beta ; y = y*s + raw*(1-s)]
  * util.py:258-276, attention.py:122-125, openaimodel.py:254-258; SR_modules.py:101-110.
- * workspace: b200sr_group_norm_workspace_bytes() bytes of device scratch.                     */
+ * workspace: b200sr_group_norm_workspace_bytes() bytes of device scratch.  Its first 1 KiB holds
+ * per-image arrival counters: zero it once after allocation; every call leaves it zeroed.
+ * Calls that may run concurrently (different streams) need distinct workspaces.                */
 size_t b200sr_group_norm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups);
 int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int32_t N, int32_t HW,
                            int32_t C, int32_t groups, float eps, int32_t silu, const void* sft_gamma,

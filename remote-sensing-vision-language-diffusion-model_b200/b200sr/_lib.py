@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sr.so")
+# B200SR_LIB selects another in-tree build of the same ABI (A/B kernel experiments); default = the product library
+LIB_PATH = os.path.join(_HERE, os.environ.get("B200SR_LIB", "libb200sr.so"))
 
 ABI_VERSION = 1
 

@@ -37,7 +37,38 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long ldo;  // elements per output row ([B*Nq, ldo], head h at columns h*64)
   float scale_log2;  // softmax scale * log2(e)
+#ifdef B200SR_ATT_TRACE
+  long long* trace;  // [4 CTAs][10 warps][64 blocks][8 events] clock64 stamps (debug builds only)
+#endif
 };
+
+#ifdef B200SR_ATT_TRACE
+static long long* g_att_trace = nullptr;
+#define ATT_T(ev)                                                                                   \
+  do {                                                                                              \
+    if (p.trace != nullptr && lane == 0 && cta_lin < 4 && j < 64)                                   \
+      p.trace[((cta_lin * 10 + warp) * 64 + j) * 8 + (ev)] = clock64();                             \
+  } while (0)
+__device__ __forceinline__ long long att_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_CTA(ev)                                                                                 \
+  do {                                                                                              \
+    if (p.trace != nullptr && threadIdx.x == 64 && cta_lin < 4096) {                                \
+      p.trace[20480 + cta_lin * 3 + (ev)] = att_gtime();                                            \
+      if ((ev) == 0) {                                                                              \
+        uint32_t smid;                                                                              \
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));                                            \
+        p.trace[20480 + cta_lin * 3 + 2] = smid;                                                    \
+      }                                                                                             \
+    }                                                                                               \
+  } while (0)
+#else
+#define ATT_T(ev) do { } while (0)
+#define ATT_CTA(ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -78,6 +109,10 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int q0 = blockIdx.x * ATT_BM;
   const int h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.Nk + ATT_BN - 1) / ATT_BN;
+#ifdef B200SR_ATT_TRACE
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#endif
+  ATT_CTA(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -113,6 +148,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
+        ATT_T(0);
         uint8_t* sK = sKV + stage * 2 * ATT_TILE_BYTES;
         uint8_t* sV = sK + ATT_TILE_BYTES;
         mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
@@ -145,6 +181,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < nblk; ++j) {
         // O += P(j) V(j)
         mbar_wait(p_full, j & 1);
+        ATT_T(0);
         tc_fence_after();
         {
           const uint32_t sV = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
@@ -158,18 +195,21 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_commit(&kv_empty[stage]);
           if (j + 1 == nblk) umma_commit(o_done);
         }
+        ATT_T(1);
         if (++stage == ATT_STAGES) {
           stage = 0;
           phase ^= 1;
         }
         if (j + 1 < nblk) {
           mbar_wait(&kv_full[stage], phase);
+          ATT_T(2);
           tc_fence_after();
           const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sKV + stage * 2 * ATT_TILE_BYTES), 16, 1024);
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k)
             umma_ss(tmem + ATT_COL_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
           umma_commit(s_full);
+          ATT_T(3);
         }
       }
     }
@@ -186,6 +226,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float l = 0.f;             // this thread's share of the running sum of exponentials
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(s_full, j & 1);
+      ATT_T(0);
       tc_fence_after();
       float s[64];
 #pragma unroll
@@ -196,6 +237,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(a[i]);
       }
       tmem_ld_wait();
+      ATT_T(1);
       const int kv_left = p.Nk - j * ATT_BN - half * 64;
       if (kv_left < 64) {
 #pragma unroll
@@ -208,6 +250,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float* xch = s_xch + (j & 1) * 256;
       xch[half * 128 + r] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      ATT_T(2);
       mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]) * p.scale_log2;
       // lazy rescale: only when the maximum grew by more than 8 (factor 256) since the last one
       const bool grow = mx > m_used + 8.0f;
@@ -237,12 +280,15 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         sum1 += e1;
         pk[i] = pack_bf16x2(e0, e1);
       }
+      ATT_T(3);
       tmem_st32(tmem + lane_base + ATT_COL_P + half * 32, pk);
       l += sum0 + sum1;
       tmem_st_wait();
+      ATT_T(4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      ATT_T(5);
     }
     // epilogue: O / l -> bf16 -> global; each thread writes 32 of the 64 output columns of its row
     float* xch = s_xch + (nblk & 1) * 256;
@@ -270,6 +316,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   }
 
+  ATT_CTA(1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -310,6 +357,9 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+#ifdef B200SR_ATT_TRACE
+  p.trace = g_att_trace;
+#endif
   const size_t smem_bytes = ATT_TILE_BYTES * (1 + 2 * ATT_STAGES) + 1024 + 128 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
@@ -325,3 +375,7 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
 }
 
 }  // namespace b200sr
+
+#ifdef B200SR_ATT_TRACE
+extern "C" void b200sr_debug_set_attn_trace(void* p) { b200sr::g_att_trace = reinterpret_cast<long long*>(p); }
+#endif

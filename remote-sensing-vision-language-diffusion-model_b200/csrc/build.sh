@@ -6,6 +6,9 @@ OUT="${HERE}/../b200sr/libb200sr.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC
        --expt-relaxed-constexpr -Xptxas -v)
+# B200SR_EXTRA_FLAGS: debug builds only (e.g. -DB200SR_ATT_TRACE for tools/attn_trace.py)
+read -r -a EXTRA <<< "${B200SR_EXTRA_FLAGS:-}"
+FLAGS+=("${EXTRA[@]}")
 mkdir -p "${HERE}/build"
 pids=()
 for f in gemm_conv attention norm elementwise capi; do

@@ -13,14 +13,25 @@
 
 namespace b200sr {
 
+static constexpr int GN_WS_COUNTER_FLOATS = 256;
+
+// sums in fp64 -> (mean, 1/sqrt(var + eps)); the variance is formed in fp64 (no cancellation), only the
+// final reciprocal square root is fp32 (correctly rounded sqrt and divide).
+__device__ __forceinline__ float2 gn_mean_rstd(double sum, double sumsq, double inv_cnt, float eps) {
+  const double mean = sum * inv_cnt;
+  double var = sumsq * inv_cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  return make_float2(static_cast<float>(mean), 1.0f / sqrtf(static_cast<float>(var) + eps));
+}  // 1 KiB of per-image arrival counters at the start of the workspace
+
 // ------------------------------------------------------------------------------------------
 // GroupNorm pass 1: per-(image, pixel-chunk, group) partial sum / sum-of-squares.
 // Thread t owns channel vector (t % C8) (8 channels, one 16-byte load per pixel) and walks
 // pixels t / C8, t / C8 + P, ... of its chunk, so consecutive threads read consecutive 16 B.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
-                int pix_per_cta, int chunks) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ workspace, int HW, int C, int groups,
+                int pix_per_cta, int chunks, int N, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_red[];  // [P][C] sums, then [P][C] sums of squares (no atomics: deterministic)
@@ -34,6 +45,10 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   const int p_end = min(HW, p_begin + pix_per_cta);
   float* s_sum = s_red;
   float* s_sq = s_red + P * C;
+  // workspace: [N] arrival counters (zero between launches) | [N][groups] (mean, rstd) | partial sums
+  unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+  float2* stats = reinterpret_cast<float2*>(workspace + GN_WS_COUNTER_FLOATS);
+  float* partial = workspace + GN_WS_COUNTER_FLOATS + 2 * static_cast<size_t>(N) * groups;
 
   float s[8], q[8];
 #pragma unroll
@@ -91,6 +106,76 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
     dst[0] = a;
     dst[1] = b;
   }
+
+  // The last CTA of image n to get here folds the image's `chunks` partials into (mean, rstd) once,
+  // so the apply pass reads 2 * groups floats instead of every CTA re-reading all partials
+  // (that re-read was half of the apply kernel's time).  Summation order is fixed -> deterministic.
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative: orders the CTA's partial-sum stores (observed through the barrier) before the arrival
+    const unsigned int prev = atomicAdd(&counters[n], 1u);
+    s_last = (prev == static_cast<unsigned int>(chunks) - 1u);
+    __threadfence();  // ... and the other CTAs' arrivals before this CTA's reads of their partial sums
+  }
+  __syncthreads();
+  if (!s_last) return;
+  const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * chunks * groups;
+  const double inv_cnt = 1.0 / (static_cast<double>(HW) * cpg);
+  const int T = blockDim.x;
+  if (T % groups == 0 && 2 * T * sizeof(double) <= 2 * static_cast<size_t>(P) * C * sizeof(float)) {
+    // thread t: group t % groups, chunk rows t / groups, + T / groups, ... (coalesced rows of float2)
+    const int g = threadIdx.x % groups, r0 = threadIdx.x / groups, rstep = T / groups;
+    double a = 0.0, b = 0.0;
+    // every load of a batch is issued before the first add: one L2 round trip per 40 rows
+    for (int k0 = r0; k0 < chunks; k0 += 40 * rstep) {
+      float2 v[40];
+#pragma unroll
+      for (int i = 0; i < 40; ++i) {
+        const int k = k0 + i * rstep;
+        v[i] = k < chunks ? __ldcg(src + static_cast<size_t>(k) * groups + g) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 40; ++i) {
+        a += v[i].x;
+        b += v[i].y;
+      }
+    }
+    double* s_d = reinterpret_cast<double*>(s_red);  // the [P][C] buffers are dead by now
+    __syncthreads();
+    s_d[threadIdx.x] = a;
+    s_d[T + threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      a = 0.0;
+      b = 0.0;
+      for (int r = 0; r < rstep; ++r) {
+        a += s_d[r * groups + threadIdx.x];
+        b += s_d[T + r * groups + threadIdx.x];
+      }
+      stats[static_cast<size_t>(n) * groups + threadIdx.x] = gn_mean_rstd(a, b, inv_cnt, eps);
+    }
+  } else {
+    // generic shapes: warp per group, lanes over chunks, fixed xor-shuffle tree
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = T >> 5;
+    for (int g = warp; g < groups; g += nwarps) {
+      double a = 0.0, b = 0.0;
+      for (int k = lane; k < chunks; k += 32) {
+        const float2 v = __ldcg(src + static_cast<size_t>(k) * groups + g);
+        a += v.x;
+        b += v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) {
+        stats[static_cast<size_t>(n) * groups + g] = gn_mean_rstd(a, b, inv_cnt, eps);
+      }
+    }
+  }
+  if (threadIdx.x == 0) counters[n] = 0u;  // ready for the next launch (and for graph replays)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -100,7 +185,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
 // ------------------------------------------------------------------------------------------
 struct GnApplyArgs {
   const __nv_bfloat16* x;
-  const float* partial;
+  const float* stats;  // [N][groups] (mean, rstd) written by the statistics pass
   const float* weight;
   const float* bias;
   __nv_bfloat16* y;
@@ -108,8 +193,7 @@ struct GnApplyArgs {
   const __nv_bfloat16* sft_beta;   // optional [N, HW, C]
   const __nv_bfloat16* raw;        // optional un-modulated tensor for the control_scale lerp
   float control_scale;
-  float eps;
-  int HW, C, groups, pix_per_cta, chunks_stats, silu;
+  int HW, C, groups, pix_per_cta, silu;
 };
 
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
@@ -124,19 +208,13 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
   const int n = blockIdx.y;
   const int cpg = C / a.groups;
 
-  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    const float* src = a.partial + (static_cast<size_t>(n) * a.chunks_stats * a.groups + g) * 2;
-    for (int k = 0; k < a.chunks_stats; ++k) {
-      s += src[static_cast<size_t>(k) * a.groups * 2];
-      q += src[static_cast<size_t>(k) * a.groups * 2 + 1];
+  {
+    const float2* stats = reinterpret_cast<const float2*>(a.stats) + static_cast<size_t>(n) * a.groups;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+      const float2 m = __ldcg(stats + g);
+      s_ab[g] = m.x;
+      s_ab[a.groups + g] = m.y;
     }
-    const double cnt = static_cast<double>(HW) * cpg;
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_ab[g] = static_cast<float>(mean);
-    s_ab[a.groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
   }
   __syncthreads();
   if (pl >= P) return;
@@ -156,9 +234,8 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
   const size_t img = static_cast<size_t>(n) * HW;
   const bool sft = a.sft_gamma != nullptr;
   const float cs = a.control_scale;
-  for (int pix = p_begin + pl; pix < p_end; pix += P) {
-    const size_t off = (img + pix) * C8 + cv;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.x) + off);
+  // one pixel-vector: normalise, activate, modulate, store
+  auto emit = [&](const size_t off, const uint4 u) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     float v[8];
 #pragma unroll
@@ -200,6 +277,20 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
     o.z = pack_bf16x2(v[4], v[5]);
     o.w = pack_bf16x2(v[6], v[7]);
     reinterpret_cast<uint4*>(a.y)[off] = o;
+  };
+  int pix = p_begin + pl;
+  // 4 independent 16-byte loads in flight per thread (a one-load-at-a-time loop ran at 1/3 of the
+  // statistics pass's speed on the same tensor)
+  for (; pix + 3 * P < p_end; pix += 4 * P) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(a.x) + (img + pix + k * P) * C8 + cv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit((img + pix + k * P) * C8 + cv, u[k]);
+  }
+  for (; pix < p_end; pix += P) {
+    const size_t off = (img + pix) * C8 + cv;
+    emit(off, __ldg(reinterpret_cast<const uint4*>(a.x) + off));
   }
 }
 
@@ -223,7 +314,7 @@ static void gn_geometry(int N, int HW, int C, int* threads, int* P, int* pix_per
 size_t group_norm_workspace_bytes(int N, int HW, int C, int groups) {
   int threads, P, ppc, chunks;
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
-  return static_cast<size_t>(N) * chunks * groups * 2 * sizeof(float);
+  return (GN_WS_COUNTER_FLOATS + 2 * static_cast<size_t>(N) * groups + static_cast<size_t>(N) * chunks * groups * 2) * sizeof(float);
 }
 
 int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int N, int HW, int C, int groups,
@@ -232,15 +323,15 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || (C % 8) != 0 || (C % groups) != 0 || C / 8 > 1024)
     return B200SR_EINVAL;
   if ((sft_gamma == nullptr) != (sft_beta == nullptr)) return B200SR_EINVAL;
-  if (workspace == nullptr) return B200SR_EINVAL;
+  if (workspace == nullptr || N > GN_WS_COUNTER_FLOATS) return B200SR_EINVAL;
   int threads, P, ppc, chunks;
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
   dim3 grid(chunks, N);
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * static_cast<size_t>(P) * C * sizeof(float), stream, 1, reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                    workspace, HW, C, groups, ppc, chunks);
+                                                                    workspace, HW, C, groups, ppc, chunks, N, eps);
   GnApplyArgs a;
   a.x = reinterpret_cast<const __nv_bfloat16*>(x);
-  a.partial = workspace;
+  a.stats = workspace + GN_WS_COUNTER_FLOATS;
   a.weight = weight;
   a.bias = bias;
   a.y = reinterpret_cast<__nv_bfloat16*>(y);
@@ -248,12 +339,10 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   a.sft_beta = reinterpret_cast<const __nv_bfloat16*>(sft_beta);
   a.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
   a.control_scale = control_scale;
-  a.eps = eps;
   a.HW = HW;
   a.C = C;
   a.groups = groups;
   a.pix_per_cta = ppc;
-  a.chunks_stats = chunks;
   a.silu = silu;
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 2 * groups * sizeof(float), stream, 1, a);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
