@@ -92,10 +92,15 @@ int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* 
 /* softmax(Q K^T * scale) V for head_dim 64 (attention.py:222-285, SR_modules.py:135-149).
  * q/k/v are column windows of row-major bf16 matrices: head h of q lives at columns
  * [q_col + 64h, q_col + 64h + 64) of a [B, Nq, ldq] matrix (so a fused QKV projection is
- * consumed in place); out is [B, Nq, ldo] with head h at columns [64h, 64h + 64).            */
+ * consumed in place); out is [B, Nq, ldo] with head h at columns [64h, 64h + 64).
+ * workspace: b200sr_attention_d64_workspace_bytes() bytes of device scratch (NULL allowed when that is
+ * 0).  The tiles of the last, partial wave of CTAs are split over the key range and merged through
+ * it; its first 2 KiB are arrival counters: zero them once after allocation, every call leaves them
+ * zeroed.  Calls that may run concurrently (different streams) need distinct workspaces.       */
+size_t b200sr_attention_d64_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t Nk);
 int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
-                         int32_t Nq, int32_t Nk, float scale, void* stream);
+                         int32_t Nq, int32_t Nk, float scale, void* workspace, void* stream);
 
 /* y = softmax(x * scale) over the first valid_cols entries of each row (the rest are written as 0: zero-
  * padded keys); x fp32 [rows, cols], y bf16.  SR3 SelfAttention (one head of width C, scores from

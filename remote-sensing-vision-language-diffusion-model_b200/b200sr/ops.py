@@ -93,8 +93,10 @@ class workspace_slot:
         return False
 
 
-def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.type, device.index, _ws_slot[0])
+def _workspace(device: torch.device, nbytes: int, kind: str = "gn") -> torch.Tensor:
+    """Zero-initialised scratch per (device, stream slot, kernel family); the kernels keep their arrival
+    counters at its start zeroed between launches, so it is reused by every call of that family."""
+    key = (device.type, device.index, _ws_slot[0], kind)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() * 4 < nbytes:
         if torch.cuda.is_current_stream_capturing() and ws is not None:
@@ -317,10 +319,13 @@ def attention(
     b, nq, ldq = q.shape
     nk = k.shape[1]
     out = torch.empty(b, nq, heads * 64, dtype=bf16, device=q.device)
+    lib = _lib.load()
+    ws_bytes = lib.b200sr_attention_d64_workspace_bytes(b, heads, nq, nk)
+    ws = _workspace(q.device, ws_bytes, "attn") if ws_bytes else None
     with _Timed("attention", 4.0 * b * heads * nq * nk * 64, f"B{b} H{heads} Nq{nq} Nk{nk}"):
-        rc = _lib.load().b200sr_attention_d64(
+        rc = lib.b200sr_attention_d64(
             q.data_ptr(), ldq, q_col, k.data_ptr(), k.shape[2], k_col, v.data_ptr(), v.shape[2], v_col, out.data_ptr(),
-            heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _stream()
+            heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _ptr(ws), _stream()
         )
     check(rc, f"attention B={b} H={heads} Nq={nq} Nk={nk}")
     return out

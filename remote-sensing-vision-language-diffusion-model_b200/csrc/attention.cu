@@ -14,6 +14,9 @@
 // the final O / l is exact).  Two CTAs are resident per SM (80 KiB smem, 256 TMEM columns each)
 // so one CTA's exponentials overlap the other's MMAs.
 //
+// Wave quantisation: with 2 CTAs per SM the grid runs in waves of 296 tiles; the tiles of a last,
+// partial wave are split over their key blocks (attention_plan) and merged by the last CTA to arrive.
+//
 // Q, K and V are addressed as column windows of row-major bf16 matrices ([B, N, ld] with a
 // column offset), so the fused QKV GEMM output is consumed in place.
 #include "common.cuh"
@@ -30,6 +33,8 @@ static constexpr int ATT_TMEM_COLS = 256;
 static constexpr int ATT_COL_S = 0;     // 128 fp32 columns
 static constexpr int ATT_COL_P = 128;   // 64 columns of packed bf16 pairs
 static constexpr int ATT_COL_O = 192;   // 64 fp32 columns
+static constexpr int ATT_PART_FLOATS = 66 * 128;  // per split partial: O^T [64][128] fp32, m [128], l [128]
+static constexpr int ATT_WS_COUNTERS = 512;       // uint32 arrival counters at the start of the workspace
 
 struct AttnParams {
   int B, H, Nq, Nk;
@@ -37,6 +42,12 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long ldo;  // elements per output row ([B*Nq, ldo], head h at columns h*64)
   float scale_log2;  // softmax scale * log2(e)
+  // Tail splitting (see attention_plan): CTAs [0, full_ctas) each own a whole 128-row tile; the
+  // remaining tiles are each shared by `split` CTAs that take `blocks_per_split` key blocks apiece,
+  // publish (O, m, l) partials to `partials` and the last to arrive merges them.
+  int n_qtiles, full_ctas, split, blocks_per_split;
+  float* partials;          // [tail tiles][split][ATT_PART_FLOATS]
+  unsigned int* counters;   // [tail tiles], zero between launches
 #ifdef B200SR_ATT_TRACE
   long long* trace;  // [4 CTAs][10 warps][64 blocks][8 events] clock64 stamps (debug builds only)
 #endif
@@ -106,11 +117,21 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* s_xch = reinterpret_cast<float*>(tmem_slot + 2);  // [2][2][128] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BM;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.Nk + ATT_BN - 1) / ATT_BN;
+  // work decode: whole tile, or one key-block range of a tail tile
+  int tile = blockIdx.x, jb0 = 0, split_idx = -1, tail_idx = 0;
+  int nblk = (p.Nk + ATT_BN - 1) / ATT_BN;  // key blocks this CTA walks (global block = jb0 + j)
+  if (static_cast<int>(blockIdx.x) >= p.full_ctas) {
+    const int t = blockIdx.x - p.full_ctas;
+    tail_idx = t / p.split;
+    split_idx = t - tail_idx * p.split;
+    tile = p.full_ctas + tail_idx;
+    jb0 = split_idx * p.blocks_per_split;
+    nblk = min(nblk - jb0, p.blocks_per_split);
+  }
+  const int q0 = (tile % p.n_qtiles) * ATT_BM;
+  const int h = (tile / p.n_qtiles) % p.H, b = tile / (p.n_qtiles * p.H);
 #ifdef B200SR_ATT_TRACE
-  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int cta_lin = blockIdx.x;
 #endif
   ATT_CTA(0);
 
@@ -152,8 +173,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint8_t* sK = sKV + stage * 2 * ATT_TILE_BYTES;
         uint8_t* sV = sK + ATT_TILE_BYTES;
         mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_3d(sK, &tmK, &kv_full[stage], p.k_col + h * ATT_D, j * ATT_BN, b);
-        tma_load_3d(sV, &tmV, &kv_full[stage], p.v_col + h * ATT_D, j * ATT_BN, b);
+        tma_load_3d(sK, &tmK, &kv_full[stage], p.k_col + h * ATT_D, (jb0 + j) * ATT_BN, b);
+        tma_load_3d(sV, &tmV, &kv_full[stage], p.v_col + h * ATT_D, (jb0 + j) * ATT_BN, b);
         if (++stage == ATT_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -238,7 +259,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       tmem_ld_wait();
       ATT_T(1);
-      const int kv_left = p.Nk - j * ATT_BN - half * 64;
+      const int kv_left = p.Nk - (jb0 + j) * ATT_BN - half * 64;
       if (kv_left < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -297,12 +318,53 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     l += xch[(half ^ 1) * 128 + r];
     mbar_wait(o_done, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
     const int q = q0 + r;
     uint32_t o[32];
     tmem_ld32(tmem + lane_base + ATT_COL_O + half * 32, o);
     tmem_ld_wait();
-    if (q < p.Nq) {
+    bool write_out = true;
+    if (split_idx >= 0) {
+      // publish this key range's partial: O (unnormalised, relative to m_used) transposed so that a warp
+      // writes 128 contiguous bytes, then the running maximum and the sum
+      float* part = p.partials + (static_cast<size_t>(tail_idx) * p.split + split_idx) * ATT_PART_FLOATS;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) part[(half * 32 + i) * 128 + r] = __uint_as_float(o[i]);
+      if (half == 0) {
+        part[64 * 128 + r] = m_used;
+        part[65 * 128 + r] = l;
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const unsigned int prev = atomicAdd(&p.counters[tail_idx], 1u);
+        tmem_slot[1] = (prev == static_cast<unsigned int>(p.split) - 1u) ? 1u : 0u;
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      write_out = tmem_slot[1] != 0u;
+      if (write_out) {
+        // last arriver: merge the partials in split order (fixed order -> deterministic)
+        const float* base = p.partials + static_cast<size_t>(tail_idx) * p.split * ATT_PART_FLOATS;
+        float m_all = -INFINITY;
+        for (int s2 = 0; s2 < p.split; ++s2) m_all = fmaxf(m_all, __ldcg(base + s2 * ATT_PART_FLOATS + 64 * 128 + r));
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        l = 0.f;
+        for (int s2 = 0; s2 < p.split; ++s2) {
+          const float* ps = base + s2 * ATT_PART_FLOATS;
+          const float w = ex2_approx(__ldcg(ps + 64 * 128 + r) - m_all);
+          l = fmaf(w, __ldcg(ps + 65 * 128 + r), l);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = fmaf(w, __ldcg(ps + (half * 32 + i) * 128 + r), acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(acc[i]);
+        if (threadIdx.x == 64) p.counters[tail_idx] = 0u;  // ready for the next launch / graph replay
+      }
+    }
+    const float inv_l = 1.0f / l;
+    if (write_out && q < p.Nq) {
       __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + q) * p.ldo + h * ATT_D + half * 32;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
@@ -330,15 +392,61 @@ static int make_map3(CUtensorMap* m, const void* base, long long ld, int rows, i
   return make_tmap_bf16(m, base, 3, dims, strides, box);
 }
 
+// Work plan.  A tile = 128 query rows of one (batch, head); 2 CTAs are resident per SM, so the grid
+// runs in waves of 2 * num_sms tiles and a last partial wave costs as much as a full one.  The tiles
+// of that last wave are therefore split over the key blocks (`split` CTAs per tile, merged by the
+// last CTA to finish) so that the tail wave is shorter by about that factor.
+struct AttnPlan {
+  int n_qtiles, tiles, full, tail, split, blocks_per_split;
+  size_t workspace_bytes;
+};
+
+static AttnPlan attention_plan(int B, int H, int Nq, int Nk) {
+  AttnPlan a;
+  a.n_qtiles = (Nq + ATT_BM - 1) / ATT_BM;
+  a.tiles = B * H * a.n_qtiles;
+  const int nblk = (Nk + ATT_BN - 1) / ATT_BN;
+  const int slots = 2 * num_sms();
+  a.full = (a.tiles / slots) * slots;
+  a.tail = a.tiles - a.full;
+  a.split = 1;
+  a.blocks_per_split = nblk;
+  if (a.tail > 0 && a.tail <= ATT_WS_COUNTERS) {
+    int s = 1;
+    while (s * 2 <= nblk && a.tail * s * 2 <= slots) s *= 2;
+    if (s > 1) {
+      a.blocks_per_split = (nblk + s - 1) / s;
+      a.split = (nblk + a.blocks_per_split - 1) / a.blocks_per_split;  // no empty key ranges
+    }
+  }
+  if (a.split == 1) {
+    a.full = a.tiles;
+    a.tail = 0;
+  }
+  a.workspace_bytes = a.tail == 0 ? 0
+                                  : ATT_WS_COUNTERS * sizeof(unsigned int) +
+                                        static_cast<size_t>(a.tail) * a.split * ATT_PART_FLOATS * sizeof(float);
+  return a;
+}
+
+size_t attention_d64_workspace_bytes(int B, int H, int Nq, int Nk) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return 0;
+  return attention_plan(B, H, Nq, Nk).workspace_bytes;
+}
+
 // q: [B, Nq, ldq] window at q_col; k, v: [B, Nk, ldk / ldv] windows; out: [B, Nq, ldo], head h at h*64.
+// workspace: attention_d64_workspace_bytes() bytes (may be null when that is 0); its first 2 KiB are
+// arrival counters that must be zero before the first call and are left zero by every call.
 int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
                   long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
-                  cudaStream_t stream) {
+                  void* workspace, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return B200SR_EINVAL;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (q_col % 8) || (k_col % 8) || (v_col % 8))
     return B200SR_EINVAL;
   if (q_col + H * ATT_D > ldq || k_col + H * ATT_D > ldk || v_col + H * ATT_D > ldv || H * ATT_D > ldo)
     return B200SR_EINVAL;
+  const AttnPlan plan = attention_plan(B, H, Nq, Nk);
+  if (plan.workspace_bytes != 0 && workspace == nullptr) return B200SR_EINVAL;
   CUtensorMap tmQ, tmK, tmV;
   int rc = make_map3(&tmQ, q, ldq, Nq, B, static_cast<int>(ldq));
   if (rc) return rc;
@@ -357,6 +465,12 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.n_qtiles = plan.n_qtiles;
+  p.full_ctas = plan.full;
+  p.split = plan.split;
+  p.blocks_per_split = plan.blocks_per_split;
+  p.counters = reinterpret_cast<unsigned int*>(workspace);
+  p.partials = reinterpret_cast<float*>(reinterpret_cast<unsigned int*>(workspace) + ATT_WS_COUNTERS);
 #ifdef B200SR_ATT_TRACE
   p.trace = g_att_trace;
 #endif
@@ -368,7 +482,7 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
       return B200SR_ELAUNCH;
     attr_set = true;
   }
-  dim3 grid((Nq + ATT_BM - 1) / ATT_BM, H, B);
+  dim3 grid(plan.full + plan.tail * plan.split);
   return launch_k(attention_d64_kernel, grid, dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmK, tmV, p) == cudaSuccess
              ? B200SR_OK
              : B200SR_ELAUNCH;

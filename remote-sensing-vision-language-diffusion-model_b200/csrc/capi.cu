@@ -81,7 +81,8 @@ int layer_norm(const void* x, void* y, const float* weight, const float* bias, i
 int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream);
 int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
                   long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
-                  cudaStream_t stream);
+                  void* workspace, cudaStream_t stream);
+size_t attention_d64_workspace_bytes(int B, int H, int Nq, int Nk);
 int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int HW, float scale, cudaStream_t stream);
 int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStream_t stream);
 int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream);
@@ -131,7 +132,7 @@ using namespace b200sr;
 
 extern "C" {
 
-int b200sr_abi_version(void) { return 1; }
+int b200sr_abi_version(void) { return 2; }
 int b200sr_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200SR_ENODEV;
@@ -177,9 +178,13 @@ int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int
 }
 int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
-                         int32_t Nq, int32_t Nk, float scale, void* stream) {
+                         int32_t Nq, int32_t Nk, float scale, void* workspace, void* stream) {
   if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return B200SR_EINVAL;
-  return attention_d64(q, ldq, q_col, k, ldk, k_col, v, ldv, v_col, out, ldo, B, H, Nq, Nk, scale, S(stream));
+  return attention_d64(q, ldq, q_col, k, ldk, k_col, v, ldv, v_col, out, ldo, B, H, Nq, Nk, scale, workspace,
+                       S(stream));
+}
+size_t b200sr_attention_d64_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t Nk) {
+  return attention_d64_workspace_bytes(B, H, Nq, Nk);
 }
 int b200sr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, float scale, void* stream) {
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;

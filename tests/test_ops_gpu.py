@@ -167,7 +167,10 @@ def test_layer_norm(ops, M, C):
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(2, 20, 1024, 1024), (2, 10, 4096, 4096), (2, 10, 4096, 77), (2, 20, 1024, 77),
-                                       (1, 2, 256, 256), (2, 5, 64, 64), (1, 3, 200, 333), (2, 4, 128, 640)])
+                                       (1, 2, 256, 256), (2, 5, 64, 64), (1, 3, 200, 333), (2, 4, 128, 640),
+                                       # tail-split plans: all tiles in the partial wave, ragged last key block / 5 key
+                                       # blocks over 3 ranges / one more tile than a full wave of 296
+                                       (1, 4, 256, 1000), (1, 2, 300, 640), (1, 33, 1152, 512)])
 def test_attention(ops, B, H, Nq, Nk):
     C = H * 64
     q = _rand(B, Nq, C, seed=1).to(bf16)
@@ -188,6 +191,23 @@ def test_attention_fused_qkv_and_peaky(ops):
     qf, kf, vf = (t.reshape(B, N, H, 64).transpose(1, 2) for t in (q, k, v))
     ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, N, C)
     assert rel_l2(out, ref) < 8e-3
+
+
+def test_attention_split_is_deterministic_and_leaves_counters_zero(ops):
+    """The last partial wave of tiles is split over the key range and merged by the last CTA to arrive:
+    repeated calls must agree bit for bit and the arrival counters must be back at zero."""
+    from b200sr import ops as _ops
+    B, H, N = 2, 20, 1024  # 320 tiles = 296 + 24 -> the 24 tail tiles are split 8 ways
+    C = H * 64
+    qkv = _rand(B, N, 3 * C, seed=7).to(bf16)
+    outs = [ops.attention(qkv, qkv, qkv, H, q_col=0, k_col=C, v_col=2 * C) for _ in range(4)]
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ws = [w for key, w in _ops._ws_cache.items() if key[-1] == "attn"]
+    assert ws, "the split plan should have asked for a workspace"
+    for w in ws:
+        assert int(w[:512].view(torch.int32).abs().sum()) == 0
 
 
 def test_layout_upsample_concat_misc(ops):
