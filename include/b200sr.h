@@ -41,6 +41,7 @@ typedef struct b200sr_epilogue {
   const float* bias;        /* [N] fp32 or NULL */
   const float* rowvec;      /* [groups, N] fp32 or NULL (ResBlock emb add, openaimodel.py:337-348) */
   int32_t rows_per_group;   /* GEMM only; 0 = single group */
+  int64_t ld_rowvec;        /* elements between rowvec rows; 0 = N (rowvec may be a column window of a wider matrix) */
   const void* residual;     /* bf16 [M, ldr] or NULL */
   int64_t ldr;
   void* out;                /* bf16 (or fp32 when out_fp32) [M, ldc] */

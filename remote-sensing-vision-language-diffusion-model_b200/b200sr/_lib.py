@@ -25,6 +25,7 @@ class Epilogue(C.Structure):
         ("bias", c_void_p),
         ("rowvec", c_void_p),
         ("rows_per_group", c_int),
+        ("ld_rowvec", c_i64),
         ("residual", c_void_p),
         ("ldr", c_i64),
         ("out", c_void_p),

@@ -102,6 +102,29 @@ def _silu_of(emb: torch.Tensor) -> torch.Tensor:
     return s
 
 
+def _project_emb_for_resblocks(holder: Packed, root: nn.Module, emb: torch.Tensor) -> None:
+    """Every ResBlock applies its own Linear to the same SiLU(emb) (openaimodel.py:281-283, :337-341).
+    They only depend on emb, so all of a network's projections run as ONE GEMM against the row-wise
+    concatenation of the weights right after emb is known; each block then reads its column window
+    (fp32 [B, sum Cout], consumed through ``ld_rowvec``) instead of launching an M = B GEMM of its own."""
+    blocks = [m for m in root.modules() if isinstance(m, ResBlock)]
+    if not blocks:
+        return
+    params = tuple(p for blk in blocks for p in (blk.emb_layers[1].weight, blk.emb_layers[1].bias))
+    w_all, b_all = holder._pk("rb_emb", params, lambda *ps: (
+        torch.cat([ops.pack_linear(w) for w in ps[0::2]], 0).contiguous(),
+        torch.cat([_F32(b) for b in ps[1::2]], 0).contiguous()))
+    proj = ops.gemm(_silu_of(emb), w_all, b_all, out_fp32=True)  # [B, sum Cout]
+    table, off = {}, 0
+    for blk in blocks:
+        table[id(blk)] = proj[:, off:off + blk.out_channels]
+        off += blk.out_channels
+    try:
+        emb._b200sr_rb = table
+    except Exception:  # pragma: no cover - exotic tensor subclasses
+        pass
+
+
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     """util.py:206-230 (cos | sin); returns bf16 [B, dim]."""
     return ops.sinusoid_embedding(timesteps, dim, max_period, sin_first=False)
@@ -199,7 +222,10 @@ class ResBlock(TimestepBlock, Packed):
 
     def forward_nhwc(self, x, emb):
         # emb add is fused into conv1's epilogue, the skip add into conv2's (openaimodel.py:337-350)
-        emb_out = _linear(self, "emb", self.emb_layers[1], _silu_of(emb), out_fp32=True)
+        pre = getattr(emb, "_b200sr_rb", None)
+        emb_out = pre.get(id(self)) if pre is not None else None
+        if emb_out is None:  # stand-alone use of the block
+            emb_out = _linear(self, "emb", self.emb_layers[1], _silu_of(emb), out_fp32=True)
         h = _gn(self.in_layers[0], x, silu=True)
         h = _conv3x3(self, "conv1", self.in_layers[2], h, rowvec=emb_out)
         h = _gn(self.out_layers[0], h, silu=True)
@@ -512,10 +538,13 @@ class UNetModel(nn.Module, Packed):
         t_emb = timestep_embedding(timesteps, self.model_channels)
         h = _linear(self, "te0", self.time_embed[0], t_emb, act=1)
         if self.num_classes is None:
-            return _linear(self, "te2", self.time_embed[2], h)
-        emb_t = _linear(self, "te2", self.time_embed[2], h)
-        l = _linear(self, "le0", self.label_emb[0][0], tokens_bf16(y), act=1)
-        return _linear(self, "le2", self.label_emb[0][2], l, residual=emb_t)
+            emb = _linear(self, "te2", self.time_embed[2], h)
+        else:
+            emb_t = _linear(self, "te2", self.time_embed[2], h)
+            l = _linear(self, "le0", self.label_emb[0][0], tokens_bf16(y), act=1)
+            emb = _linear(self, "le2", self.label_emb[0][2], l, residual=emb_t)
+        _project_emb_for_resblocks(self, self, emb)
+        return emb
 
     def _out_nchw_f32(self, h_nhwc):
         """self.out: GN32 + SiLU + 3x3 conv to the latent channels, written as fp32 NCHW (openaimodel.py:941-947)."""

@@ -149,6 +149,7 @@ def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, g
     e.bias = _ptr(bias)
     e.rowvec = _ptr(rowvec)
     e.rows_per_group = rows_per_group
+    e.ld_rowvec = rowvec.stride(0) if rowvec is not None and rowvec.dim() == 2 else 0
     e.residual = _ptr(residual)
     e.ldr = ldr
     e.out = out.data_ptr()

@@ -114,6 +114,7 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.bias = e->bias;
   a.rowvec = e->rowvec;
   a.rows_per_group = e->rows_per_group;
+  a.ld_rowvec = e->ld_rowvec;
   a.residual = e->residual;
   a.ldr = e->ldr;
   a.out = e->out;

@@ -299,6 +299,7 @@ struct EpilogueArgs {
   const float* bias;
   const float* rowvec;
   int rows_per_group;
+  long long ld_rowvec;  // 0 = N
   const void* residual;
   long long ldr;
   void* out;

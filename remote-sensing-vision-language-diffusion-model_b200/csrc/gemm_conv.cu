@@ -56,6 +56,7 @@ struct GemmParams {
   const float* bias;
   const float* rowvec;
   int rows_per_group;
+  long long ld_rowvec;
   const __nv_bfloat16* residual;
   long long ldr;
   void* out;
@@ -365,7 +366,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       const bool has_res = p.residual != nullptr && valid;
       const __nv_bfloat16* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
-      const float* rv_row = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.N + n0 : nullptr;
+      const float* rv_row = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
       uint4 res_cur[4], res_nxt[4];
       if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
       if (has_res) {
@@ -577,6 +578,8 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.bias = e.bias;
   p.rowvec = e.rowvec;
   p.rows_per_group = e.rows_per_group;
+  p.ld_rowvec = e.ld_rowvec != 0 ? e.ld_rowvec : p.N;
+  if (e.rowvec != nullptr && ((p.ld_rowvec % 4) != 0 || p.ld_rowvec < p.N)) return B200SR_EINVAL;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(e.residual);
   p.ldr = e.ldr;
   p.out = e.out;
