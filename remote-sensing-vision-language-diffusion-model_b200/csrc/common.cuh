@@ -230,7 +230,14 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ------------------------------------------------------------------------------------------
 // small numeric helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with ex2.approx / rcp.approx (a full-precision divide is ~8 instructions; the GroupNorm
+// apply pass is issue-bound on them).  exp(-x) -> inf for very negative x gives x * 0 = -0, as the exact form.
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 // Exact (erf) GELU, attention.py:84-91 via F.gelu.  erf by Abramowitz & Stegun 7.1.28,
 //   erf(t) = 1 - (1 + a1 t + ... + a6 t^6)^-16,  |error| <= 3e-7 for t >= 0,
 // branch-free and 11 instructions shorter than erff(): the GEGLU GEMM is bound by its epilogue's
