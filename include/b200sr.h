@@ -50,6 +50,18 @@ typedef struct b200sr_epilogue {
   int32_t geglu;
   float alpha;
   int32_t act;              /* 0 = none, 1 = SiLU applied to the final value (ZeroSFT mlp_shared, SR_modules.py:75-78) */
+  /* Cross-attention against a context that is constant over the sampler steps (the text embedding,
+   * attention.py:222-285), with to_q folded into the keys and to_out into the values:
+   *   P = softmax_per_head(x K'^T)   one GEMM, N = heads * 80, epilogue = softmax over each 80-column
+   *                                  segment of a row, of which the first softmax_valid (77) take part
+   *                                  (the others are written as 0); exp2 is applied to the accumulator
+   *                                  as is, i.e. K' carries scale * log2(e)
+   *   out = P V' + bias + residual   a plain GEMM with K = heads * 80
+   * K' / V' differ per batch element: rows [g * w_rows_per_group, (g + 1) * w_rows_per_group) of A are
+   * multiplied with weight rows [g * w_group_stride, g * w_group_stride + N).                          */
+  int32_t softmax_valid;       /* 0 = off; GEMM only, bf16 output, no other epilogue term */
+  int32_t w_rows_per_group;    /* 0 = one weight for all rows; otherwise a multiple of 256 */
+  int64_t w_group_stride;      /* in weight rows */
 } b200sr_epilogue;
 
 /* D = A[M,K] * W[N,K]^T with fused epilogue; bf16 operands, fp32 accumulate (tcgen05 / TMEM).

@@ -34,6 +34,9 @@ class Epilogue(C.Structure):
         ("geglu", c_int),
         ("alpha", c_float),
         ("act", c_int),
+        ("softmax_valid", c_int),
+        ("w_rows_per_group", c_int),
+        ("w_group_stride", c_i64),
     ]
 
 

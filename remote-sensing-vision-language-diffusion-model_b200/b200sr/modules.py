@@ -314,8 +314,40 @@ class CrossAttention(nn.Module, Packed):
             return
         old = table.get(id(context))
         shape = (*context.shape[:-1], 2 * self.to_q.weight.shape[0])
-        out = old[1] if (old is not None and old[0] is context and tuple(old[1].shape) == shape) else None
-        table[id(context)] = (context, ops.gemm(context, self._wkv(), out=out))
+        same = old is not None and old[0] is context and tuple(old[1].shape) == shape
+        kv = ops.gemm(context, self._wkv(), out=old[1] if same else None)
+        fused = self._fold_projections(context)
+        if same and old[2] is not None and fused is not None:
+            for dst, src in zip(old[2], fused):
+                dst.copy_(src)
+            fused = old[2]
+        table[id(context)] = (context, kv, fused)
+
+    SEG = 80  # key slots per head in the folded form (77 text tokens, padded)
+
+    @torch.no_grad()
+    def _fold_projections(self, context: torch.Tensor):
+        """With a context that is constant over the steps, to_q folds into the keys and to_out into the values:
+            softmax(x Wq^T K_h^T * s) V_h Wo_h^T  =  softmax(x K'_h^T) V'_h,   K'_h = s K_h Wq_h,  V'_h = V_h Wo_h^T
+        so a cross-attention is two GEMMs (the first with a per-head softmax epilogue) instead of q-projection +
+        attention + out-projection.  One-time fp32 preparation per bound context, like weight packing.
+        Returns (K' [B, H*80, C] bf16 in log2 units, V'^T [B, C, H*80] bf16, number of keys) or None."""
+        b, tk = context.shape[0], context.shape[1]
+        if context.dim() != 3 or tk > self.SEG:
+            return None
+        h, c = self.heads, self.to_q.weight.shape[1]
+        ctx = context.float()
+        k = (ctx @ self.to_k.weight.float().t()).view(b, tk, h, 64)
+        v = (ctx @ self.to_v.weight.float().t()).view(b, tk, h, 64)
+        wq = self.to_q.weight.float().view(h, 64, c)
+        wo = self.to_out[0].weight.float().view(-1, h, 64)
+        kp = torch.zeros(b, h, self.SEG, c, device=context.device)
+        kp[:, :, :tk] = torch.einsum("bjhd,hdc->bhjc", k, wq) * (self.scale * 1.4426950408889634)
+        vp = torch.zeros(b, h, self.SEG, wo.shape[0], device=context.device)
+        vp[:, :, :tk] = torch.einsum("bjhd,chd->bhjc", v, wo)
+        return (kp.reshape(b, h * self.SEG, c).to(bf16).contiguous(),
+                vp.reshape(b, h * self.SEG, -1).transpose(1, 2).to(bf16).contiguous(),
+                torch.tensor(tk))
 
     def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
                 residual: Optional[torch.Tensor] = None, alpha: float = 1.0, kv: Optional[torch.Tensor] = None):
@@ -323,6 +355,13 @@ class CrossAttention(nn.Module, Packed):
             raise NotImplementedError("masks / additional tokens / cross-frame attention are not on the hot path")
         x = tokens_bf16(x)
         ctx = tokens_bf16(context) if context is not None else None
+        if ctx is not None and kv is None and x.dim() == 3 and x.shape[1] % 256 == 0:
+            bound = self.__dict__.get("_static", {}).get(id(ctx))
+            if bound is not None and bound[0] is ctx and bound[2] is not None and bound[2][0].shape[0] == x.shape[0]:
+                k_fold, v_fold, tk = bound[2]
+                p = ops.gemm(x, k_fold, softmax_valid=int(tk), w_rows_per_group=x.shape[1])
+                bias = self._pk("out.b", (self.to_out[0].bias,), _F32)
+                return ops.gemm(p, v_fold, bias, residual=residual, alpha=alpha, w_rows_per_group=x.shape[1])
         return _linear(self, "out", self.to_out[0], self.attend(x, ctx, kv), residual=residual, alpha=alpha)
 
 

@@ -144,7 +144,8 @@ def pack_geglu(weight: torch.Tensor, bias: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # dense contractions
 # ------------------------------------------------------------------------------------------------
-def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act=0) -> Epilogue:
+def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act=0,
+              softmax_valid=0, w_rows_per_group=0, w_group_stride=0) -> Epilogue:
     e = Epilogue()
     e.bias = _ptr(bias)
     e.rowvec = _ptr(rowvec)
@@ -158,6 +159,9 @@ def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, g
     e.geglu = int(geglu)
     e.alpha = float(alpha)
     e.act = int(act)
+    e.softmax_valid = int(softmax_valid)
+    e.w_rows_per_group = int(w_rows_per_group)
+    e.w_group_stride = int(w_group_stride)
     return e
 
 
@@ -175,15 +179,24 @@ def gemm(
     out: Optional[torch.Tensor] = None,
     out_fp32: bool = False,
     force_bn: int = 0,
+    softmax_valid: int = 0,
+    w_rows_per_group: int = 0,
 ) -> torch.Tensor:
     """``out = alpha * (a @ w.T + bias) + rowvec[group] + residual`` (or GEGLU).  a: [..., K] bf16
     (last-dim contiguous, uniform row stride), w: [N, K] packed bf16.  `out` may be a column
-    slice of a wider row-major tensor (its row stride is honoured)."""
+    slice of a wider row-major tensor (its row stride is honoured).
+    `w_rows_per_group` > 0: w is [G, N, K] and rows [g * w_rows_per_group, ...) of a use w[g] (per-batch-element
+    operands).  `softmax_valid` > 0: the epilogue is a row softmax (base 2, no scale) over each 80-column segment
+    of which the first `softmax_valid` columns take part; output bf16 probabilities."""
     _req(w, bf16, "gemm.w")
     if a.dtype != bf16 or not a.is_cuda:
         raise _lib.B200SRError("gemm.a: expected CUDA bf16")
     K = a.shape[-1]
-    N = w.shape[0]
+    N = w.shape[-2]
+    w_group_stride = 0
+    if w_rows_per_group:
+        assert w.dim() == 3 and w.is_contiguous() and w.shape[0] * w_rows_per_group >= a.numel() // K
+        w_group_stride = N
     a2 = a.reshape(-1, K)
     if a2.stride(-1) != 1:
         a2 = a2.contiguous()
@@ -199,7 +212,8 @@ def gemm(
         r2 = residual if residual.dim() == 2 else residual.reshape(-1, residual.shape[-1])
         assert r2.dtype == bf16 and r2.stride(-1) == 1
         ldr = r2.stride(0)
-    e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act)
+    e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act,
+                  softmax_valid, w_rows_per_group, w_group_stride)
     with _Timed("gemm", 2.0 * M * N * K, f"M{M} N{N} K{K}{' geglu' if geglu else ''}"):
         rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
     check(rc, f"gemm M={M} N={N} K={K}")

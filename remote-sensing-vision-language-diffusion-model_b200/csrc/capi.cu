@@ -123,6 +123,9 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.geglu = e->geglu;
   a.alpha = e->alpha;
   a.act = e->act;
+  a.softmax_valid = e->softmax_valid;
+  a.w_rows_per_group = e->w_rows_per_group;
+  a.w_group_stride = e->w_group_stride;
   return a;
 }
 

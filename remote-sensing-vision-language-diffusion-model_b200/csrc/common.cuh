@@ -335,6 +335,9 @@ struct EpilogueArgs {
   int geglu;
   float alpha;
   int act;  // 0 = none, 1 = SiLU (applied last)
+  int softmax_valid;        // > 0: epilogue = row softmax over each 80-column segment (first softmax_valid columns)
+  int w_rows_per_group;     // > 0: rows [g * w_rows_per_group, ...) of A use weight rows offset by g * w_group_stride
+  long long w_group_stride;
 };
 
 }  // namespace b200sr

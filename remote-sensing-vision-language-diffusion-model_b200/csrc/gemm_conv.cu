@@ -65,7 +65,12 @@ struct GemmParams {
   int geglu;
   float alpha;
   int act;
+  int softmax_valid;
+  int w_rows_per_group;
+  long long w_group_stride;
 };
+
+static constexpr int SOFTMAX_SEG = 80;  // columns per head segment in the softmax epilogue (77 text tokens, padded)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -208,7 +213,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int work = work0; work < num_work; work += work_stride) {
         const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
         const int n_blk = work / m_groups;
-        const int n0 = n_blk * p.BN + static_cast<int>(rank) * b_rows;  // this CTA's rows of the weight tile
+        int n0 = n_blk * p.BN + static_cast<int>(rank) * b_rows;  // this CTA's rows of the weight tile
+        if (p.w_rows_per_group > 0)  // per-batch-element weights stacked along the rows
+          n0 += static_cast<int>((static_cast<long long>(m_blk) * BLOCK_M / p.w_rows_per_group) * p.w_group_stride);
         int w0 = 0, h0 = 0, i0 = 0;
         if (p.mode != 0) {
           const int tw = m_blk % p.tiles_w;
@@ -377,9 +384,57 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STAGE_COLS;
+      if (p.softmax_valid > 0) {
+        // Row softmax over each SOFTMAX_SEG-column head segment of the accumulator (logits already in log2
+        // units), written as bf16 probabilities; columns >= softmax_valid of a segment are padding -> 0.
+        for (int sg = 0; sg * SOFTMAX_SEG < p.BN; ++sg) {
+          const int col0 = n0 + sg * SOFTMAX_SEG;
+          if (col0 >= p.N) break;
+          uint32_t a0[32], a1[32], a2[16];
+          tmem_ld32(t_row + sg * SOFTMAX_SEG, a0);
+          tmem_ld32(t_row + sg * SOFTMAX_SEG + 32, a1);
+          tmem_ld16(t_row + sg * SOFTMAX_SEG + 64, a2);
+          tmem_ld_wait();
+          float v[SOFTMAX_SEG];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(a0[j]);
+            v[32 + j] = __uint_as_float(a1[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[64 + j] = __uint_as_float(a2[j]);
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < SOFTMAX_SEG; ++j) {
+            if (j >= p.softmax_valid) v[j] = -INFINITY;
+            mx = fmaxf(mx, v[j]);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < SOFTMAX_SEG; ++j) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[j] - mx));
+            v[j] = e;
+            sum += e;
+          }
+          const float inv = 1.0f / sum;
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0);
+#pragma unroll
+            for (int q = 0; q < SOFTMAX_SEG / 8; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(v[q * 8 + 0] * inv, v[q * 8 + 1] * inv);
+              u.y = pack_bf16x2(v[q * 8 + 2] * inv, v[q * 8 + 3] * inv);
+              u.z = pack_bf16x2(v[q * 8 + 4] * inv, v[q * 8 + 5] * inv);
+              u.w = pack_bf16x2(v[q * 8 + 6] * inv, v[q * 8 + 7] * inv);
+              dst[q] = u;
+            }
+          }
+        }
+      }
       uint32_t a_cur[32], a_nxt[32];
-      tmem_ld32(t_row, a_cur);
-      for (int c = 0; c < p.BN; c += 32) {
+      if (p.softmax_valid <= 0) tmem_ld32(t_row, a_cur);
+      for (int c = 0; c < (p.softmax_valid > 0 ? 0 : p.BN); c += 32) {
         tmem_ld_wait();
         const bool more = c + 32 < p.BN;
         if (more) {
@@ -588,6 +643,14 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.geglu = e.geglu;
   p.alpha = e.alpha;
   p.act = e.act;
+  p.softmax_valid = e.softmax_valid;
+  p.w_rows_per_group = e.w_rows_per_group;
+  p.w_group_stride = e.w_group_stride;
+  if (e.softmax_valid < 0 || e.softmax_valid > SOFTMAX_SEG) return B200SR_EINVAL;
+  if (e.softmax_valid > 0 && (e.geglu || e.out_fp32 || e.residual != nullptr || e.rowvec != nullptr || e.bias != nullptr ||
+                              e.act != 0 || (p.N % SOFTMAX_SEG) != 0))
+    return B200SR_EINVAL;
+  if (e.w_rows_per_group < 0 || (e.w_rows_per_group % (2 * BLOCK_M)) != 0) return B200SR_EINVAL;
   if (e.geglu && e.act) return B200SR_EINVAL;
   if (e.out == nullptr) return B200SR_EINVAL;
   if (e.geglu && (e.out_fp32 || e.residual != nullptr || e.rowvec != nullptr || (p.N % 32) != 0)) return B200SR_EINVAL;
@@ -602,10 +665,16 @@ static int finish(const CUtensorMap& tmA, const void* W, GemmParams& p, int real
   const int cluster = real_m_blocks >= 2 ? 2 : 1;
   p.num_m_blocks = ((real_m_blocks + cluster - 1) / cluster) * cluster;
   p.BN = force_bn > 0 ? force_bn : pick_bn(real_m_blocks, p.N, p.k_iters, num_sms(), cluster);
-  if (p.BN % 32 != 0 || p.BN > 256 || p.BN <= 0) return B200SR_EINVAL;
+  if (p.softmax_valid > 0) p.BN = p.N >= 3 * SOFTMAX_SEG ? 3 * SOFTMAX_SEG : p.N;  // whole head segments per tile
+  if (p.BN % (p.softmax_valid > 0 ? 16 : 32) != 0 || p.BN > 256 || p.BN <= 0) return B200SR_EINVAL;
   p.num_n_blocks = (p.N + p.BN - 1) / p.BN;
   CUtensorMap tmB;
-  uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+  // stacked per-group weights: the map spans every group's rows
+  const long long w_rows = p.w_rows_per_group > 0
+                               ? ((static_cast<long long>(p.M) + p.w_rows_per_group - 1) / p.w_rows_per_group - 1) *
+                                         p.w_group_stride + p.N
+                               : p.N;
+  uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows)};
   uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
   uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN / cluster)};
   const int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);

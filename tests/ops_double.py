@@ -18,8 +18,17 @@ bf16 = torch.bfloat16
 
 
 def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu=False, alpha=1.0, act=0, out=None,
-         out_fp32=False, force_bn=0):
-    y = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
+         out_fp32=False, force_bn=0, softmax_valid=0, w_rows_per_group=0):
+    a2 = a.float().reshape(-1, a.shape[-1])
+    if w_rows_per_group:
+        y = torch.cat([a2[g * w_rows_per_group:(g + 1) * w_rows_per_group] @ w[g].float().t()
+                       for g in range((a2.shape[0] + w_rows_per_group - 1) // w_rows_per_group)], 0)
+    else:
+        y = a2 @ w.float().t()
+    if softmax_valid:
+        seg = y.view(y.shape[0], -1, 80).clone()
+        seg[:, :, softmax_valid:] = float("-inf")
+        y = torch.softmax(seg * math.log(2.0), dim=-1).reshape(y.shape[0], -1)
     if bias is not None:
         y = y + bias
     if geglu:

@@ -193,6 +193,26 @@ def test_attention_fused_qkv_and_peaky(ops):
     assert rel_l2(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("B,T,C,H,Tk", [(2, 1024, 1280, 20, 77), (2, 4096, 640, 10, 77), (1, 256, 128, 2, 33)])
+def test_gemm_grouped_weights_and_head_softmax_epilogue(ops, B, T, C, H, Tk):
+    """Folded cross-attention building blocks: per-batch-element weights (w_rows_per_group) and the per-head
+    softmax epilogue over 80-column segments (first Tk columns valid, base 2, pad -> 0)."""
+    x = _rand(B, T, C, seed=1).to(bf16)
+    kf = (_rand(B, H * 80, C, seed=2) * 0.08).to(bf16)
+    p = ops.gemm(x, kf, softmax_valid=Tk, w_rows_per_group=T)
+    logits = torch.einsum("btc,bnc->btn", x.float(), kf.float()).view(B, T, H, 80)
+    logits[..., Tk:] = float("-inf")
+    ref = torch.softmax(logits * math.log(2.0), dim=-1).reshape(B, T, H * 80)
+    assert p.shape == ref.shape and rel_l2(p, ref) < 8e-3
+    assert float(p.view(B, T, H, 80)[..., Tk:].abs().max()) == 0.0
+    vf = (_rand(B, C, H * 80, seed=3) * 0.1).to(bf16)
+    bias = _rand(C, seed=4) * 0.1
+    res = _rand(B, T, C, seed=5).to(bf16)
+    out = ops.gemm(p, vf, bias, residual=res, alpha=0.7, w_rows_per_group=T)
+    ref2 = 0.7 * (torch.einsum("btn,bcn->btc", p.float(), vf.float()) + bias) + res.float()
+    assert rel_l2(out, ref2) < 8e-3
+
+
 def test_attention_split_is_deterministic_and_leaves_counters_zero(ops):
     """The last partial wave of tiles is split over the key range and merged by the last CTA to arrive:
     repeated calls must agree bit for bit and the arrival counters must be back at zero."""

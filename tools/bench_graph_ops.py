@@ -75,6 +75,18 @@ if which in ("all", "gemm"):
     conv_case(2, 32, 32, 1280, 1280, 17)
     conv_case(2, 128, 128, 320, 320, 11)
     conv_case(2, 64, 64, 640, 640, 9)
+if which == "xattn":
+    for (B, T, C, H) in ((2, 1024, 1280, 20), (2, 4096, 640, 10)):
+        x = r(B, T, C); kf = [r(B, H * 80, C, scale=0.05) for _ in range(8)]; vf = [r(B, C, H * 80, scale=0.1) for _ in range(8)]
+        bias = torch.randn(C, device=dev); res = r(B, T, C)
+        p_ = ops.gemm(x, kf[0], softmax_valid=77, w_rows_per_group=T)
+        t1 = graph_time(lambda i: ops.gemm(x, kf[i % 8], softmax_valid=77, w_rows_per_group=T))
+        t2 = graph_time(lambda i: ops.gemm(p_, vf[i % 8], bias, residual=res, w_rows_per_group=T))
+        rows.append((f"xattn gemm1 softmax B{B} T{T} C{C}", t1, 2.0 * B * T * H * 80 * C / t1 / 1e6, 0))
+        rows.append((f"xattn gemm2 B{B} T{T} C{C}", t2, 2.0 * B * T * H * 80 * C / t2 / 1e6, 0))
+    gemm_case(2048, 10240, 1280, geglu=True, n_in_step=90)
+    gemm_case(2048, 1280, 1280, residual=True, n_in_step=293)
+    gemm_case(2048, 3840, 1280, n_in_step=90)
 if which in ("all", "attn"):
     attn_case(2, 20, 1024, 1024, 91)
     attn_case(2, 10, 4096, 4096, 15)
