@@ -163,3 +163,20 @@ def test_full_model_eps_1024(full):
     err = rel_l2(eps, ref)
     print(f"full-model eps rel-L2 vs fp32 oracle: {err:.4e}; |eps| std {ref.std().item():.3f}")
     assert err < 1e-2
+    # The engine binds the text context once per image (K/V hoisted, to_q / to_out folded into them: every
+    # text cross-attention becomes two GEMMs).  Same tolerance against the same oracle output.
+    from b200sr.modules import CrossAttention, bind_text_context
+
+    cin_b = dict(cin)
+    cin_b["crossattn"] = ctx = cin["crossattn"].to(torch.bfloat16).contiguous()  # bound by tensor identity
+    bind_text_context(full, ctx)
+    try:
+        folded = [m for m in full.modules() if isinstance(m, CrossAttention) and m.__dict__.get("_static")]
+        assert len(folded) >= 90 and all(v[2] is not None for m in folded for v in m.__dict__["_static"].values())
+        with torch.no_grad():
+            eps_b = full(net_x, idx, cin_b, 1.0, "none", None)
+    finally:
+        bind_text_context(full, None)
+    err_b = rel_l2(eps_b, ref)
+    print(f"full-model eps rel-L2 vs fp32 oracle, text context bound (folded cross-attention): {err_b:.4e}")
+    assert err_b < 1e-2
