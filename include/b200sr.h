@@ -60,6 +60,9 @@ typedef struct b200sr_epilogue {
    * K' / V' differ per batch element: rows [g * w_rows_per_group, (g + 1) * w_rows_per_group) of A are
    * multiplied with weight rows [g * w_group_stride, g * w_group_stride + N).                          */
   int32_t softmax_valid;       /* 0 = off; GEMM only, bf16 output, no other epilogue term */
+  int32_t w_dynamic;           /* set when W is an activation written by an earlier kernel on the stream (e.g. K or V of
+                                  an attention expressed as GEMMs): constant weights are otherwise prefetched before the
+                                  kernel's programmatic dependency on its predecessor resolves */
   int32_t w_rows_per_group;    /* 0 = one weight for all rows; otherwise a multiple of 256 */
   int64_t w_group_stride;      /* in weight rows */
 } b200sr_epilogue;

@@ -35,6 +35,7 @@ class Epilogue(C.Structure):
         ("alpha", c_float),
         ("act", c_int),
         ("softmax_valid", c_int),
+        ("w_dynamic", c_int),
         ("w_rows_per_group", c_int),
         ("w_group_stride", c_i64),
     ]

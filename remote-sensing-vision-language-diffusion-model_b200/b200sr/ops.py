@@ -145,7 +145,7 @@ def pack_geglu(weight: torch.Tensor, bias: torch.Tensor):
 # dense contractions
 # ------------------------------------------------------------------------------------------------
 def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act=0,
-              softmax_valid=0, w_rows_per_group=0, w_group_stride=0) -> Epilogue:
+              softmax_valid=0, w_rows_per_group=0, w_group_stride=0, w_dynamic=False) -> Epilogue:
     e = Epilogue()
     e.bias = _ptr(bias)
     e.rowvec = _ptr(rowvec)
@@ -160,6 +160,7 @@ def _epilogue(out, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, g
     e.alpha = float(alpha)
     e.act = int(act)
     e.softmax_valid = int(softmax_valid)
+    e.w_dynamic = int(w_dynamic)
     e.w_rows_per_group = int(w_rows_per_group)
     e.w_group_stride = int(w_group_stride)
     return e
@@ -181,13 +182,16 @@ def gemm(
     force_bn: int = 0,
     softmax_valid: int = 0,
     w_rows_per_group: int = 0,
+    w_dynamic: bool = False,
 ) -> torch.Tensor:
     """``out = alpha * (a @ w.T + bias) + rowvec[group] + residual`` (or GEGLU).  a: [..., K] bf16
     (last-dim contiguous, uniform row stride), w: [N, K] packed bf16.  `out` may be a column
     slice of a wider row-major tensor (its row stride is honoured).
     `w_rows_per_group` > 0: w is [G, N, K] and rows [g * w_rows_per_group, ...) of a use w[g] (per-batch-element
     operands).  `softmax_valid` > 0: the epilogue is a row softmax (base 2, no scale) over each 80-column segment
-    of which the first `softmax_valid` columns take part; output bf16 probabilities."""
+    of which the first `softmax_valid` columns take part; output bf16 probabilities.
+    `w_dynamic`: w was written by an earlier kernel on this stream (an activation used as the B operand): the
+    kernel then must not prefetch it ahead of its programmatic dependency."""
     _req(w, bf16, "gemm.w")
     if a.dtype != bf16 or not a.is_cuda:
         raise _lib.B200SRError("gemm.a: expected CUDA bf16")
@@ -213,7 +217,7 @@ def gemm(
         assert r2.dtype == bf16 and r2.stride(-1) == 1
         ldr = r2.stride(0)
     e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act,
-                  softmax_valid, w_rows_per_group, w_group_stride)
+                  softmax_valid, w_rows_per_group, w_group_stride, w_dynamic)
     with _Timed("gemm", 2.0 * M * N * K, f"M{M} N{N} K{K}{' geglu' if geglu else ''}"):
         rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
     check(rc, f"gemm M={M} N={N} K={K}")

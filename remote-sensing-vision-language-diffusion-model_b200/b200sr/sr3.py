@@ -162,10 +162,10 @@ class SelfAttention(nn.Module, Packed):
                 tok = torch.zeros(tp, c, dtype=bf16, device=x.device)
                 tok[:t].copy_(n[i])
             q, k = ops.gemm(tok, wq), ops.gemm(tok, wk)            # [T, C]
-            v_t = ops.gemm(wv, tok)                                # [C, T]  (V transposed: B operand of P @ V)
-            s = ops.gemm(q, k, out_fp32=True)                      # [T, T] fp32 scores
+            v_t = ops.gemm(wv, tok, w_dynamic=True)                          # [C, T]  (V transposed: B operand of P @ V)
+            s = ops.gemm(q, k, out_fp32=True, w_dynamic=True)                # [T, T] fp32 scores
             p = ops.softmax_rows(s, 1.0 / math.sqrt(c), valid_cols=t)
-            o_i = ops.gemm(p, v_t)                                 # [T, C]
+            o_i = ops.gemm(p, v_t, w_dynamic=True)                           # [T, C]
             outs.append(o_i if tp == t else o_i[:t].contiguous())
         o = outs[0].unsqueeze(0) if b == 1 else torch.stack(outs, 0)
         y = _linear(self, "out", self.out, o.reshape(b, h * w, c), residual=x.view(b, h * w, c))
@@ -341,6 +341,51 @@ class GaussianDiffusion(nn.Module):
             noise = torch.randn_like(x)
         return ops.sr3_update(x, eps, noise if t > 0 else None, self._step_table[t])
 
+    use_graphs = True  # one CUDA graph per (shape): ~150 launches of a step replayed in one go
+
+    @torch.no_grad()
+    def _p_sample_graphed(self, x, t, condition_x=None, noise=None):
+        """p_sample through a captured CUDA graph: the per-step scalars, the noise level and the noise are copied into
+        static buffers, then the whole step (concat, UNet, update kernel) replays.  At t = 0 the noise buffer is zero,
+        which equals the reference's `noise = zeros` branch (diffusion.py:174)."""
+        key = (tuple(x.shape), None if condition_x is None else tuple(condition_x.shape))
+        table = self.__dict__.setdefault("_graph_state", {})
+        st = table.get(key)
+        if st is None:
+            st = table[key] = {"x": torch.empty_like(x), "noise": torch.zeros_like(x),
+                               "cond": None if condition_x is None else torch.empty_like(condition_x),
+                               "level": torch.empty(x.shape[0], 1, dtype=torch.float32, device=x.device),
+                               "scal": torch.empty(self._step_table.shape[1], dtype=torch.float32, device=x.device),
+                               "graph": None, "cond_src": None}
+        st["x"].copy_(x)
+        if condition_x is not None and st["cond_src"] is not condition_x:
+            st["cond"].copy_(condition_x)
+            st["cond_src"] = condition_x
+        if t > 0:
+            st["noise"].copy_(noise) if noise is not None else st["noise"].normal_()
+        else:
+            st["noise"].zero_()
+        st["level"].copy_(self._levels[t].reshape(1, 1).expand(x.shape[0], 1))
+        st["scal"].copy_(self._step_table[t])
+
+        def body():
+            inp = torch.cat([st["cond"], st["x"]], dim=1) if st["cond"] is not None else st["x"]
+            st["out"] = ops.sr3_update(st["x"], self.denoise_fn(inp, st["level"]), st["noise"], st["scal"])
+
+        if st["graph"] is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()  # eager warm-up: packs the weights, sizes the workspaces
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            st["graph"] = g
+        st["graph"].replay()
+        return st["out"].clone()
+
     @torch.no_grad()
     def p_sample_loop(self, x_in, continous=False, noises: Optional[List[torch.Tensor]] = None):
         """diffusion.py:178-201.  `noises` (optional) = [initial image, noise of step 0, 1, ...] for reproducible runs."""
@@ -350,8 +395,9 @@ class GaussianDiffusion(nn.Module):
         shape = x_in.shape if self.conditional else x_in
         img = noises[0].to(device) if noises is not None else torch.randn(shape, device=device)
         ret_img = x_in if self.conditional else img
+        step = self._p_sample_graphed if (self.use_graphs and img.is_cuda) else self.p_sample
         for k, i in enumerate(reversed(range(0, self.num_timesteps))):
-            img = self.p_sample(img, i, condition_x=cond, noise=None if noises is None else noises[1 + k].to(device))
+            img = step(img, i, condition_x=cond, noise=None if noises is None else noises[1 + k].to(device))
             if i % sample_inter == 0:
                 ret_img = torch.cat([ret_img, img], dim=0)
         return ret_img if continous else ret_img[-1]

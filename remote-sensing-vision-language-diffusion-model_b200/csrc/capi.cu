@@ -124,6 +124,7 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.alpha = e->alpha;
   a.act = e->act;
   a.softmax_valid = e->softmax_valid;
+  a.w_dynamic = e->w_dynamic;
   a.w_rows_per_group = e->w_rows_per_group;
   a.w_group_stride = e->w_group_stride;
   return a;

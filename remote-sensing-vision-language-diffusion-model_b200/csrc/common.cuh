@@ -336,6 +336,7 @@ struct EpilogueArgs {
   float alpha;
   int act;  // 0 = none, 1 = SiLU (applied last)
   int softmax_valid;        // > 0: epilogue = row softmax over each 80-column segment (first softmax_valid columns)
+  int w_dynamic;            // != 0: the W operand is produced by an earlier kernel (no prefetch ahead of griddepcontrol.wait)
   int w_rows_per_group;     // > 0: rows [g * w_rows_per_group, ...) of A use weight rows offset by g * w_group_stride
   long long w_group_stride;
 };

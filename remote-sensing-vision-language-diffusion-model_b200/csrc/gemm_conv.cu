@@ -66,6 +66,7 @@ struct GemmParams {
   float alpha;
   int act;
   int softmax_valid;
+  int w_dynamic;
   int w_rows_per_group;
   long long w_group_stride;
 };
@@ -228,7 +229,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // Weights never depend on the previous kernel: on the first tile their first `stages` chunks are
         // requested before griddepcontrol.wait, the activation (A) chunks after it.
         const bool first = (work == work0);
-        const int pre = first ? (p.k_iters < stages ? p.k_iters : stages) : 0;
+        const int pre = (first && !p.w_dynamic) ? (p.k_iters < stages ? p.k_iters : stages) : 0;
         for (int it = 0; it < p.k_iters + pre; ++it) {
           // it in [0, pre): weight chunk `it` only; it in [pre, 2*pre): activation chunk it-pre only;
           // afterwards: both for chunk it-pre.
@@ -644,6 +645,7 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.alpha = e.alpha;
   p.act = e.act;
   p.softmax_valid = e.softmax_valid;
+  p.w_dynamic = e.w_dynamic;
   p.w_rows_per_group = e.w_rows_per_group;
   p.w_group_stride = e.w_group_stride;
   if (e.softmax_valid < 0 || e.softmax_valid > SOFTMAX_SEG) return B200SR_EINVAL;

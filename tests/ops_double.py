@@ -18,7 +18,7 @@ bf16 = torch.bfloat16
 
 
 def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu=False, alpha=1.0, act=0, out=None,
-         out_fp32=False, force_bn=0, softmax_valid=0, w_rows_per_group=0):
+         out_fp32=False, force_bn=0, softmax_valid=0, w_rows_per_group=0, w_dynamic=False):
     a2 = a.float().reshape(-1, a.shape[-1])
     if w_rows_per_group:
         y = torch.cat([a2[g * w_rows_per_group:(g + 1) * w_rows_per_group] @ w[g].float().t()

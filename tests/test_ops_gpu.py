@@ -213,6 +213,34 @@ def test_gemm_grouped_weights_and_head_softmax_epilogue(ops, B, T, C, H, Tk):
     assert rel_l2(out, ref2) < 8e-3
 
 
+def test_gemm_dynamic_w_operand_inside_a_graph(ops):
+    """An activation used as the B operand (SR3's single-head attention computes Q K^T and P V as GEMMs) must not be
+    prefetched ahead of the kernel's programmatic dependency: inside a CUDA graph the producer is still running."""
+    x = _rand(4096, 512, seed=1).to(bf16)
+    wq = (_rand(512, 512, seed=2) * 0.05).to(bf16)
+    wk = (_rand(512, 512, seed=3) * 0.05).to(bf16)
+    xs = torch.empty_like(x)
+
+    def chain():
+        q, k = ops.gemm(xs, wq), ops.gemm(xs, wk)
+        return ops.gemm(q, k, out_fp32=True, w_dynamic=True)
+
+    xs.copy_(x)
+    chain()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        s_g = chain()
+    for scale in (1.0, -0.5, 2.0):  # new producer outputs every replay: a stale prefetch of k would show
+        xs.copy_(x * scale)
+        g.replay()
+        torch.cuda.synchronize()
+        q = (xs.float() @ wq.float().t()).to(bf16).float()
+        k = (xs.float() @ wk.float().t()).to(bf16).float()
+        assert rel_l2(s_g, q @ k.t()) < 8e-3
+        assert torch.equal(s_g, chain())
+
+
 def test_attention_split_is_deterministic_and_leaves_counters_zero(ops):
     """The last partial wave of tiles is split over the key range and merged by the last CTA to arrive:
     repeated calls must agree bit for bit and the arrival counters must be back at zero."""

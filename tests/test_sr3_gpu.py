@@ -45,6 +45,10 @@ def test_unet_and_loop_match_reference_golden(net):
     psnr = 10 * math.log10(4.0 / mse)
     print(f"sr3 50-step PSNR vs reference: {psnr:.1f} dB")
     assert psnr >= 40.0
+    # the loop above replays one CUDA graph per step; the eager launch sequence must give the same bits
+    diff.use_graphs = False
+    sr_eager = diff.p_sample_loop(cond.cuda(), continous=False, noises=seq)
+    assert torch.equal(sr, sr_eager)
 
 
 def test_unet_128_vs_oracle(net):
