@@ -163,10 +163,19 @@ class Stage2Engine:
         if self.hoist_text_kv and hasattr(self.wrapper, "modules"):
             from .modules import bind_text_context
 
-            bind_text_context(self.wrapper, self.cond["crossattn"])
-            if self.split_cfg:
-                for ch in self.cond_half:
-                    bind_text_context(self.wrapper, ch["crossattn"])
+            # Binding projects / folds the text context for every cross-attention: only when the text actually
+            # changed (the tiled sampler calls set_condition per tile with the same caption and a new control slice).
+            # The source tensors are kept referenced, so "same object, same version" cannot be a recycled address.
+            prev = getattr(self, "_bound_text", None)
+            same = (prev is not None and prev[0] is c["crossattn"] and prev[1] is uc["crossattn"]
+                    and prev[2] == (c["crossattn"]._version, uc["crossattn"]._version) and prev[3] is self.cond["crossattn"])
+            if not same:
+                bind_text_context(self.wrapper, self.cond["crossattn"])
+                if self.split_cfg:
+                    for ch in self.cond_half:
+                        bind_text_context(self.wrapper, ch["crossattn"])
+                self._bound_text = (c["crossattn"], uc["crossattn"], (c["crossattn"]._version, uc["crossattn"]._version),
+                                    self.cond["crossattn"])
         self.reset_cache()
 
     def reset_cache(self):
