@@ -28,6 +28,7 @@
 // image), alpha scale, +residual[M, N], SiLU, GEGLU (value/gate interleaved in 16-column groups by
 // the weight packer), bf16 or fp32 output.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200sr {
 
@@ -36,6 +37,23 @@ static constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 static constexpr int UMMA_K = 16;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 static constexpr int MAX_STAGES = 8;
+// One pipeline stage = KSUB 64-wide K chunks (modes 0-2) or HALO_TAPS weight tiles (mode 3): the MMA issue thread
+// pays ~150-230 cycles per barrier wait + commit (tools/micro/issue_overhead.cu), which at N <= 192 exceeds the
+// MMAs' own time when it is paid per chunk.
+static constexpr int KSUB = 2;
+static constexpr int HALO_TAPS = 3;
+// mode 3 ("halo" 3x3 convolution, stride 1): per 64-channel chunk ONE (16+2) x (8+2)-pixel halo tile of the input
+// is staged and the nine taps read it as shifted windows (UMMA descriptor start + (kh * 10 + kw) * 128 B, 8-row
+// groups 10 pixel rows = 1280 B apart; the 128B swizzle is a function of the absolute address, so shifted
+// windows of a TMA-written tile are valid operands — tools/micro/shifted_desc.cu).  The activation tile then
+// crosses L2 -> SM once instead of nine times; weights stream through their own ring.
+static constexpr int HALO_TILE_W = 8, HALO_TILE_H = 16;
+static constexpr int HALO_W = HALO_TILE_W + 2, HALO_H = HALO_TILE_H + 2;
+static constexpr int A_HALO_TX_BYTES = HALO_W * HALO_H * BLOCK_K * 2;  // 23040 B written by the TMA box
+static constexpr int A_HALO_BYTES = 23 * 1024;                         // stage stride (1024-aligned)
+static constexpr int MAX_A_HALO_STAGES = 4;
+static constexpr int MAX_B_STAGES = 16;
+static constexpr int BAR_REGION_BYTES = 512;
 static constexpr int GEMM_THREADS = 192;
 static constexpr int TMEM_COLS = 512;
 static constexpr int ACC_STAGE_COLS = 256;
@@ -52,6 +70,10 @@ struct GemmParams {
   int bw_log2, bh_log2, bn_log2;
   int tiles_w, tiles_h, tiles_n;
   int stages;
+  int a_stages;  // mode 3: halo-tile ring depth (stages = weight ring depth)
+#ifdef B200SR_GEMM_TRACE
+  long long* trace;  // [grid][4]: mainloop cycles, cycles blocked on the full barrier, chunks, chunks found not ready
+#endif
   // epilogue
   const float* bias;
   const float* rowvec;
@@ -156,17 +178,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // per-CTA stage: 128 rows of A and this CTA's BN / kCluster rows of the weight tile
-  const int stage_bytes = A_STAGE_BYTES + (p.BN / kCluster) * (BLOCK_K * 2);
+  const int b_sub_bytes = (p.BN / kCluster) * (BLOCK_K * 2);      // one 64-wide weight tile of this CTA
+  const int b_stage_bytes = HALO_TAPS * b_sub_bytes;               // mode 3 weight-ring stage
+  const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);    // modes 0-2: [A0 | A1 | B0 | B1]
   const int stages = p.stages;
+  const bool halo = p.mode == 3;
   const uint32_t rank = kCluster > 1 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
+  // modes 0-2: one ring of (A tile | weight tile) stages; mode 3: a ring of halo tiles, then a ring of weight tiles
+  const int ring_bytes = halo ? p.a_stages * A_HALO_BYTES + stages * b_stage_bytes : stages * stage_bytes;
+  uint8_t* smem_b = smem + p.a_stages * A_HALO_BYTES;  // mode 3 weight ring
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);   // [16]
+  uint64_t* empty_bar = full_bar + MAX_B_STAGES;                          // [16]
+  uint64_t* a_full = empty_bar + MAX_B_STAGES;                            // [4]  mode 3
+  uint64_t* a_empty = a_full + MAX_A_HALO_STAGES;                         // [4]  mode 3
+  uint64_t* tmem_full = a_empty + MAX_A_HALO_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_epi = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);  // [4 warps][256] staged bias
+  float* s_epi = reinterpret_cast<float*>(smem + ring_bytes + BAR_REGION_BYTES);  // [4 warps][256] staged bias
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -174,6 +204,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's expect_tx arrive; bytes of both CTAs are counted here
       mbar_init(&empty_bar[s], 1);  // one (multicast) commit from the MMA issuer
+    }
+    if (halo) {
+      for (int s = 0; s < p.a_stages; ++s) {
+        mbar_init(&a_full[s], 1);
+        mbar_init(&a_empty[s], 1);
+      }
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -204,13 +240,136 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int work_stride = gridDim.x / kCluster;
   const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
 
-  if (warp == 0) {
+  if (warp == 0 && halo) {
+    // ================================ TMA producer, halo convolution ================================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int b_rows = p.BN / kCluster;
+      const uint32_t a_tx = static_cast<uint32_t>(A_HALO_TX_BYTES) * kCluster;
+      const uint32_t b_tx = static_cast<uint32_t>(b_stage_bytes) * kCluster;
+      for (int work = work0; work < num_work; work += work_stride) {
+        const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
+        const int n_blk = work / m_groups;
+        const int n0 = n_blk * p.BN + static_cast<int>(rank) * b_rows;
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int tn = m_blk / (p.tiles_w * p.tiles_h);
+        const bool first = (work == work0);
+        // weights do not depend on the previous kernel: the first tile's first weight tiles go out before the wait
+        const int b_pre = first ? (stages < 3 ? stages : 3) : 0;
+        // weight ring: one stage = the HALO_TAPS weight tiles of one kernel row (kh) of one channel chunk
+        auto load_b = [&](int cc, int kh) {
+          mbar_wait(&empty_bar[sb], pb ^ 1);
+          uint8_t* dst = smem_b + sb * b_stage_bytes;
+          if (leader) mbar_expect_tx(&full_bar[sb], b_tx);
+#pragma unroll
+          for (int kw = 0; kw < HALO_TAPS; ++kw) {
+            const int kb = (kh * 3 + kw) * p.Cin + cc * BLOCK_K;
+            if (kCluster == 1)
+              tma_load_2d(dst + kw * b_sub_bytes, &tmB, &full_bar[sb], kb, n0);
+            else
+              tma2_load_2d(dst + kw * b_sub_bytes, &tmB, mapa_cluster(smem_u32(&full_bar[sb]), 0), kb, n0);
+          }
+          if (++sb == stages) {
+            sb = 0;
+            pb ^= 1;
+          }
+        };
+        for (int kh = 0; kh < b_pre; ++kh) load_b(0, kh);
+        if (first) pdl_wait();
+        for (int cc = 0; cc < p.kc_per_tap; ++cc) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          uint8_t* dst = smem + sa * A_HALO_BYTES;
+          if (kCluster == 1) {
+            mbar_expect_tx(&a_full[sa], a_tx);
+            tma_load_4d(dst, &tmA, &a_full[sa], cc * BLOCK_K, tw * HALO_TILE_W - 1, th * HALO_TILE_H - 1, tn);
+          } else {
+            if (leader) mbar_expect_tx(&a_full[sa], a_tx);
+            tma2_load_4d(dst, &tmA, mapa_cluster(smem_u32(&a_full[sa]), 0), cc * BLOCK_K, tw * HALO_TILE_W - 1,
+                         th * HALO_TILE_H - 1, tn);
+          }
+          if (++sa == p.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+          for (int kh = (cc == 0 ? b_pre : 0); kh < 3; ++kh) load_b(cc, kh);
+        }
+      }
+    }
+  } else if (warp == 1 && halo) {
+    // ================================ MMA issuer, halo convolution ================================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M * kCluster, static_cast<uint32_t>(p.BN), 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ready = false;
+      for (int work = work0; work < num_work; work += work_stride) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STAGE_COLS;
+        for (int cc = 0; cc < p.kc_per_tap; ++cc) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_base = smem_u32(smem + sa * A_HALO_BYTES);
+          for (int kh = 0; kh < 3; ++kh) {
+            if (!ready) mbar_wait(&full_bar[sb], pb);
+            tc_fence_after();
+            {  // probe the next weight stage now, consume the answer after this row's MMAs are issued
+              const int ns = sb + 1 == stages ? 0 : sb + 1;
+              ready = mbar_test_wait(&full_bar[ns], ns == 0 ? pb ^ 1 : pb);
+            }
+            const uint32_t b_base = smem_u32(smem_b + sb * b_stage_bytes);
+#pragma unroll
+            for (int kw = 0; kw < HALO_TAPS; ++kw) {
+              // window of tap (kh, kw): start (kh * 10 + kw) pixel rows in; 8-pixel groups one halo row (1280 B) apart
+              const uint64_t adesc = umma_smem_desc_sw128(a_base + (kh * HALO_W + kw) * 128, 16, HALO_W * 128);
+              const uint64_t bdesc = umma_smem_desc_sw128(b_base + kw * b_sub_bytes, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                if (kCluster == 1)
+                  umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | kh | kw | k) != 0);
+                else
+                  umma2_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | kh | kw | k) != 0);
+              }
+            }
+            if (kCluster == 1)
+              umma_commit(&empty_bar[sb]);
+            else
+              umma2_commit_mc(&empty_bar[sb], 3);
+            if (++sb == stages) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          if (kCluster == 1)
+            umma_commit(&a_empty[sa]);
+          else
+            umma2_commit_mc(&a_empty[sa], 3);
+          if (++sa == p.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        if (kCluster == 1)
+          umma_commit(&tmem_full[acc]);
+        else
+          umma2_commit_mc(&tmem_full[acc], 3);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes) * kCluster;
+      const uint32_t sub_tx = static_cast<uint32_t>(A_STAGE_BYTES + b_sub_bytes) * kCluster;  // bytes of one K chunk, both CTAs
       const int b_rows = p.BN / kCluster;
+      const int s_iters = (p.k_iters + KSUB - 1) / KSUB;  // pipeline stages per tile
       for (int work = work0; work < num_work; work += work_stride) {
         const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
         const int n_blk = work / m_groups;
@@ -226,58 +385,63 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           h0 = th * bh;
           i0 = tn << p.bn_log2;
         }
-        // Weights never depend on the previous kernel: on the first tile their first `stages` chunks are
-        // requested before griddepcontrol.wait, the activation (A) chunks after it.
+        // Weights never depend on the previous kernel: on the first tile the weight chunks of the first `pre`
+        // stages are requested before griddepcontrol.wait, the activation (A) chunks after it.
         const bool first = (work == work0);
-        const int pre = (first && !p.w_dynamic) ? (p.k_iters < stages ? p.k_iters : stages) : 0;
-        for (int it = 0; it < p.k_iters + pre; ++it) {
-          // it in [0, pre): weight chunk `it` only; it in [pre, 2*pre): activation chunk it-pre only;
-          // afterwards: both for chunk it-pre.
+        const int pre = (first && !p.w_dynamic) ? (s_iters < stages ? s_iters : stages) : 0;
+        for (int it = 0; it < s_iters + pre; ++it) {
+          // it in [0, pre): weights of stage `it` only; it in [pre, 2*pre): activations of stage it-pre only;
+          // afterwards: both for stage it-pre.
           const bool w_only = it < pre, a_only = (it >= pre && it < 2 * pre);
-          const int kit = w_only ? it : it - pre;
+          const int sit = w_only ? it : it - pre;
           if (it == pre && first) pdl_wait();
-          if (!first && it == 0) { /* later tiles: everything already ordered after the wait */ }
-          const int st = w_only || a_only ? kit : stage;
+          const int st = w_only || a_only ? sit : stage;
           if (!w_only && !a_only) mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + st * stage_bytes;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          if (leader && !a_only) mbar_expect_tx(&full_bar[st], tx_bytes);
-          int kb;  // K coordinate of the weight tile
-          int tap = 0, c0 = 0, kh = 0, kw = 0;
-          if (p.mode == 0) {
-            kb = kit * BLOCK_K;
-          } else {
-            tap = kit / p.kc_per_tap;
-            c0 = (kit - tap * p.kc_per_tap) * BLOCK_K;
-            kh = tap / 3;
-            kw = tap - kh * 3;
-            kb = tap * p.Cin + c0;
-          }
-          // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
-          const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
-          if (kCluster == 1) {
-            if (!w_only) {
-              if (p.mode == 0)
-                tma_load_2d(sa, &tmA, &full_bar[st], kb, m_blk * BLOCK_M);
-              else if (p.mode == 1)
-                tma_load_4d(sa, &tmA, &full_bar[st], c0, w0 + kw - 1, h0 + kh - 1, i0);
-              else
-                tma_load_5d(sa, &tmA, &full_bar[st], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+          const int nsub = p.k_iters - sit * KSUB < KSUB ? p.k_iters - sit * KSUB : KSUB;
+          uint8_t* sa0 = smem + st * stage_bytes;
+          uint8_t* sb0 = sa0 + KSUB * A_STAGE_BYTES;
+          if (leader && !a_only) mbar_expect_tx(&full_bar[st], sub_tx * nsub);
+          const uint32_t bar = kCluster > 1 ? mapa_cluster(smem_u32(&full_bar[st]), 0) : 0u;  // the leader's barrier
+          for (int j = 0; j < nsub; ++j) {
+            const int kit = sit * KSUB + j;
+            uint8_t* sa = sa0 + j * A_STAGE_BYTES;
+            uint8_t* sb = sb0 + j * b_sub_bytes;
+            int kb;  // K coordinate of the weight tile
+            int tap = 0, c0 = 0, kh = 0, kw = 0;
+            if (p.mode == 0) {
+              kb = kit * BLOCK_K;
+            } else {
+              tap = kit / p.kc_per_tap;
+              c0 = (kit - tap * p.kc_per_tap) * BLOCK_K;
+              kh = tap / 3;
+              kw = tap - kh * 3;
+              kb = tap * p.Cin + c0;
             }
-            if (!a_only) tma_load_2d(sb, &tmB, &full_bar[st], kb, n0);
-          } else {
-            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[st]), 0);  // the leader's barrier
-            if (!w_only) {
-              if (p.mode == 0)
-                tma2_load_2d(sa, &tmA, bar, kb, m_blk * BLOCK_M);
-              else if (p.mode == 1)
-                tma2_load_4d(sa, &tmA, bar, c0, w0 + kw - 1, h0 + kh - 1, i0);
-              else
-                tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+            // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
+            const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
+            if (kCluster == 1) {
+              if (!w_only) {
+                if (p.mode == 0)
+                  tma_load_2d(sa, &tmA, &full_bar[st], kb, m_blk * BLOCK_M);
+                else if (p.mode == 1)
+                  tma_load_4d(sa, &tmA, &full_bar[st], c0, w0 + kw - 1, h0 + kh - 1, i0);
+                else
+                  tma_load_5d(sa, &tmA, &full_bar[st], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+              }
+              if (!a_only) tma_load_2d(sb, &tmB, &full_bar[st], kb, n0);
+            } else {
+              if (!w_only) {
+                if (p.mode == 0)
+                  tma2_load_2d(sa, &tmA, bar, kb, m_blk * BLOCK_M);
+                else if (p.mode == 1)
+                  tma2_load_4d(sa, &tmA, bar, c0, w0 + kw - 1, h0 + kh - 1, i0);
+                else
+                  tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+              }
+              if (!a_only) tma2_load_2d(sb, &tmB, bar, kb, n0);
             }
-            if (!a_only) tma2_load_2d(sb, &tmB, bar, kb, n0);
           }
-          if (w_only) continue;  // the ring position advances once per chunk (with its activation load)
+          if (w_only) continue;  // the ring position advances once per stage (with its activation loads)
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -293,24 +457,53 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // The issue thread is the mainloop's critical resource (tools/micro/issue_overhead.cu: wait + 4 MMAs + commit
+      // = ~550 cycles per chunk against a 320-cycle MMA floor at N = 160), so the NEXT chunk's barrier is probed
+      // before this chunk's MMAs are issued and the answer is consumed afterwards: the probe's latency hides
+      // under the issue, and the blocking wait runs only when the data really is not there yet.
+      bool ready = false;
+#ifdef B200SR_GEMM_TRACE
+      long long t_loop = 0, t_wait = 0, n_chunks = 0, n_late = 0;
+#endif
       for (int work = work0; work < num_work; work += work_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STAGE_COLS;
-        for (int it = 0; it < p.k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+#ifdef B200SR_GEMM_TRACE
+        const long long t_begin = clock64();
+#endif
+        const int s_iters = (p.k_iters + KSUB - 1) / KSUB;
+        for (int it = 0; it < s_iters; ++it) {
+          const int nsub = p.k_iters - it * KSUB < KSUB ? p.k_iters - it * KSUB : KSUB;
+#ifdef B200SR_GEMM_TRACE
+          n_chunks += nsub;
+          if (!ready) {
+            const long long t0 = clock64();
+            mbar_wait(&full_bar[stage], phase);
+            t_wait += clock64() - t0;
+            ++n_late;
+          }
+#else
+          if (!ready) mbar_wait(&full_bar[stage], phase);
+#endif
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t adesc = umma_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(sb, 16, 1024);
+          {
+            const int ns = stage + 1 == stages ? 0 : stage + 1;
+            ready = mbar_test_wait(&full_bar[ns], ns == 0 ? phase ^ 1 : phase);
+          }
+          const uint32_t sa0 = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb0 = sa0 + KSUB * A_STAGE_BYTES;
+          for (int j = 0; j < nsub; ++j) {
+            const uint64_t adesc = umma_smem_desc_sw128(sa0 + j * A_STAGE_BYTES, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(sb0 + j * b_sub_bytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
-            if (kCluster == 1)
-              umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-            else
-              umma2_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
+              if (kCluster == 1)
+                umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | j | k) != 0);
+              else
+                umma2_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | j | k) != 0);
+            }
           }
           // free the smem slot (in both CTAs of a pair) once these MMAs retire
           if (kCluster == 1)
@@ -322,6 +515,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             phase ^= 1;
           }
         }
+#ifdef B200SR_GEMM_TRACE
+        t_loop += clock64() - t_begin;
+        if (p.trace != nullptr) {
+          p.trace[blockIdx.x * 4 + 0] = t_loop;
+          p.trace[blockIdx.x * 4 + 1] = t_wait;
+          p.trace[blockIdx.x * 4 + 2] = n_chunks;
+          p.trace[blockIdx.x * 4 + 3] = n_late;
+        }
+#endif
         // accumulator complete -> epilogue warps (of both CTAs of a pair)
         if (kCluster == 1)
           umma_commit(&tmem_full[acc]);
@@ -605,16 +807,38 @@ static int pick_bn(int m_blocks, int N, int k_iters, int sms, int cluster) {
   return best;
 }
 
+#ifdef B200SR_GEMM_TRACE
+static long long* g_gemm_trace = nullptr;
+#endif
+
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - 4096 /*epilogue bias staging*/;
-  const int stage_bytes = A_STAGE_BYTES + (p.BN / kCluster) * BLOCK_K * 2;
-  int stages = smem_budget / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > p.k_iters + 1) stages = p.k_iters + 1;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256 + 4096;
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/;
+  const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
+  const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
+  size_t ring_bytes;
+  if (p.mode == 3) {
+    const int b_stage_bytes = HALO_TAPS * b_sub_bytes;
+    p.a_stages = p.kc_per_tap >= 2 ? 2 : 1;
+    int stages = (smem_budget - p.a_stages * A_HALO_BYTES) / b_stage_bytes;
+    if (stages > MAX_B_STAGES) stages = MAX_B_STAGES;
+    if (stages < 2) return B200SR_EINVAL;
+    p.stages = stages;
+    ring_bytes = static_cast<size_t>(p.a_stages) * A_HALO_BYTES + static_cast<size_t>(stages) * b_stage_bytes;
+  } else {
+    const int s_iters = (p.k_iters + KSUB - 1) / KSUB;
+    int stages = smem_budget / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages > s_iters + 1) stages = s_iters + 1;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    p.a_stages = 0;
+    ring_bytes = static_cast<size_t>(stages) * stage_bytes;
+  }
+  const size_t smem_bytes = ring_bytes + 1024 + BAR_REGION_BYTES + 4096;
+#ifdef B200SR_GEMM_TRACE
+  p.trace = g_gemm_trace;
+#endif
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -718,8 +942,19 @@ int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, in
   int bh = 1;
   while (bw * bh * 2 <= 128 && bh < OH) bh *= 2;
   int bn = 128 / (bw * bh);
+  // stride-1 convolutions on images at least one 8 x 16 tile large take the halo path (mode 3)
+  static const bool halo_enabled = [] {
+    const char* e = getenv("B200SR_CONV_HALO");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool halo = halo_enabled && stride == 1 && (W % HALO_TILE_W) == 0 && H >= HALO_TILE_H;
+  if (halo) {
+    bw = HALO_TILE_W;
+    bh = HALO_TILE_H;
+    bn = 1;
+  }
   GemmParams p{};
-  p.mode = stride == 1 ? 1 : 2;
+  p.mode = halo ? 3 : (stride == 1 ? 1 : 2);
   p.NB = NB;
   p.OH = OH;
   p.OW = OW;
@@ -744,6 +979,10 @@ int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, in
     uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
                            static_cast<uint64_t>(H) * W * Cin * 2};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    if (halo) {
+      box[1] = HALO_W;
+      box[2] = HALO_H;
+    }
     rc = make_tmap_bf16(&tmA, x, 4, dims, strides, box);
   } else {
     // [NB, H/2, 2, W/2, 2*Cin]: (w parity, channel) merge into one contiguous dim of 2*Cin
@@ -760,3 +999,7 @@ int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, in
 }
 
 }  // namespace b200sr
+
+#ifdef B200SR_GEMM_TRACE
+extern "C" void b200sr_debug_set_gemm_trace(void* p) { b200sr::g_gemm_trace = reinterpret_cast<long long*>(p); }
+#endif
