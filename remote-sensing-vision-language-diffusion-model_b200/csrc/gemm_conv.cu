@@ -892,6 +892,8 @@ static int finish(const CUtensorMap& tmA, const void* W, GemmParams& p, int real
   p.num_m_blocks = ((real_m_blocks + cluster - 1) / cluster) * cluster;
   p.BN = force_bn > 0 ? force_bn : pick_bn(real_m_blocks, p.N, p.k_iters, num_sms(), cluster);
   if (p.softmax_valid > 0) p.BN = p.N >= 3 * SOFTMAX_SEG ? 3 * SOFTMAX_SEG : p.N;  // whole head segments per tile
+  // halo convolution: two weight stages of three taps each must fit next to the halo ring
+  if (p.mode == 3 && cluster == 1 && p.BN > 192 && force_bn <= 0) p.BN = 192;
   if (p.BN % (p.softmax_valid > 0 ? 16 : 32) != 0 || p.BN > 256 || p.BN <= 0) return B200SR_EINVAL;
   p.num_n_blocks = (p.N + p.BN - 1) / p.BN;
   CUtensorMap tmB;

@@ -96,6 +96,8 @@ def test_gemm_geglu(ops, M, C):
      # halo-tile path (stride 1, W % 8 == 0, H >= 16): partial tiles in H, odd image counts (cluster round-up),
      # 1 / 3 / 5 channel chunks (halo ring of depth 1 / 2 wrapping), Cout not a multiple of the N tile
      (3, 40, 8, 64, 72, 1), (1, 16, 24, 192, 128, 1), (5, 48, 16, 320, 256, 1), (1, 17, 8, 128, 64, 1),
+     (1, 16, 8, 64, 512, 1),  # a single M block (no CTA pair) with a wide N tile
+    
      (2, 32, 32, 64, 64, 2), (2, 128, 128, 320, 320, 2), (2, 16, 16, 128, 128, 2), (1, 8, 8, 64, 64, 2)],
 )
 def test_conv3x3(ops, N, H, W, Cin, Cout, stride):
