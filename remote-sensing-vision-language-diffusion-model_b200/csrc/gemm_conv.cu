@@ -10,23 +10,30 @@
 //   mode 0  GEMM      A is a row-major [M, K] matrix (tokens x channels / NHWC pixels x channels)
 //   mode 1  conv3x3   A is an NHWC image; the K loop runs over 9 taps x Cin/64 chunks and each
 //                     chunk is one 4-D TMA box shifted by the tap offset (zero fill = padding 1)
+//                     (images smaller than one 8 x 16 tile)
 //   mode 2  conv3x3 stride 2 (Downsample): the image is viewed as [N, H/2, 2, W/2, 2*C] so each
 //                     tap is again one rectangular 5-D TMA box
+//   mode 3  conv3x3 stride 1, "halo": per 64-channel chunk one (16+2) x (8+2)-pixel halo tile is staged and
+//                     the nine taps read it as shifted windows of the same shared-memory tile, so the
+//                     activation crosses L2 -> SM once instead of nine times; weights have their own ring
 //
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM owner,
 // warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Two accumulator
 // stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1.
 //
-// With one 128 x BN tile per SM the mainloop is shared-memory-bandwidth bound (TMA writes plus the
-// SS-mode operand reads need ~190 B/cycle/SM against 128 available; measured 40-50 % tensor-pipe
-// activity, and TMA multicast of the weight tile inside a 2-CTA cluster changed nothing), so CTAs
-// run as CTA pairs (kCluster = 2, tcgen05 cta_group::2): one 256 x BN UMMA spans both SMs, each
+// CTAs run as CTA pairs (kCluster = 2, tcgen05 cta_group::2): one 256 x BN UMMA spans both SMs, each
 // CTA stages its own 128 rows of A and only HALF of the weight tile, and the leader CTA issues
 // the MMAs for both.  Problems with a single M block use kCluster = 1 (cta_group::1).
 //
+// What bounds the mainloop (measured): the MMA issue thread pays 150-230 cycles per
+// barrier wait + commit, more than the MMAs of one 64-wide chunk take at N <= 192, so a pipeline stage holds two
+// K chunks (three taps in mode 3) and the next stage's barrier is probed before the current MMAs are issued;
+// beyond that, GEMM operands arrive from L2 at ~14 TB/s chip-wide whatever the tile shape.
+//
 // Fused epilogues: +bias[N], +rowvec[group, N] (ResBlock timestep-embedding add, one group per
-// image), alpha scale, +residual[M, N], SiLU, GEGLU (value/gate interleaved in 16-column groups by
-// the weight packer), bf16 or fp32 output.
+// image; may be a column window of a wider matrix), alpha scale, +residual[M, N], SiLU, GEGLU (value/gate
+// interleaved in 16-column groups by the weight packer), per-head row softmax (folded text cross-attention),
+// per-row-group weights (per-batch-element B operands), bf16 or fp32 output.
 #include "common.cuh"
 #include <cstdlib>
 
