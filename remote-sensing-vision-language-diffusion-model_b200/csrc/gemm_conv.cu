@@ -28,7 +28,8 @@
 // What bounds the mainloop (measured): the MMA issue thread pays 150-230 cycles per
 // barrier wait + commit, more than the MMAs of one 64-wide chunk take at N <= 192, so a pipeline stage holds two
 // K chunks (three taps in mode 3) and the next stage's barrier is probed before the current MMAs are issued;
-// beyond that, GEMM operands arrive from L2 at ~14 TB/s chip-wide whatever the tile shape.
+// beyond that the mainloop is bound by shared-memory bandwidth (128 B/clk: TMA writes + UMMA operand reads, e.g.
+// 80 KB per chunk at N = 256 -> 625 cycles against a 512-cycle MMA floor).
 //
 // Fused epilogues: +bias[N], +rowvec[group, N] (ResBlock timestep-embedding add, one group per
 // image; may be a column window of a wider matrix), alpha scale, +residual[M, N], SiLU, GEGLU (value/gate
