@@ -135,6 +135,14 @@ def test_uncached_step_engine_vs_oracle(small):
     # compare the update direction (x_next - x), which is what the network contributes
     assert rel_l2(out - x, ref - x) < 1e-2
     assert psnr(out, ref) >= 40.0
+    # the other engine schedules compute the same step within the same tolerance: single stream without graphs (the
+    # adapters' control-side work is then fused differently, so not bit-identical), CFG halves on separate streams
+    for kw in ({"dual_stream": False, "use_graphs": False}, {"split_cfg": True}):
+        alt = Stage2Engine(small, **kw)
+        alt.set_condition(c, uc)
+        out_alt, _ = alt.step(x, 3, noise, 0.0)
+        assert rel_l2(out_alt - x, ref - x) < 1e-2
+        assert rel_l2(out_alt - x, out - x) < 5e-3
 
 
 @pytest.fixture(scope="module")
