@@ -51,13 +51,16 @@ def test_unet_and_loop_match_reference_golden(net):
     assert torch.equal(sr, sr_eager)
 
 
-def test_unet_128_vs_oracle(net):
-    """BASELINE config 1 size (x8, 16^2 -> 128^2): one UNet call vs the fp32 oracle on the GPU."""
+@pytest.mark.parametrize("size", [128, 512])
+def test_unet_vs_oracle(net, size):
+    """BASELINE config 1 size (x8, 16^2 -> 128^2) and a 512^2 image (mid-block attention over 1024 tokens of width
+    512, computed as GEMMs + row softmax; the 1024^2 case of config 3 is tools/sr3_1024.py): one UNet call vs the
+    fp32 oracle on the GPU."""
     from oracle import inputs, sr3 as osr3
 
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    cond, noises = inputs.sr3_inputs(size=128, seed=0, steps=1)
+    cond, noises = inputs.sr3_inputs(size=size, seed=0, steps=1)
     x = torch.cat([cond, noises[0]], dim=1).cuda()
     level = torch.tensor([[0.42]], device="cuda")
     sd = {k: v.detach() for k, v in net.state_dict().items()}
@@ -65,5 +68,5 @@ def test_unet_128_vs_oracle(net):
         ref = osr3.unet(sd, "", x, level)
         out = net(x, level)
     err = rel_l2(out, ref)
-    print(f"sr3 128^2 eps rel-L2 vs fp32 oracle: {err:.4e}")
+    print(f"sr3 {size}^2 eps rel-L2 vs fp32 oracle: {err:.4e}")
     assert err < 1e-2
