@@ -407,10 +407,16 @@ static AttnPlan attention_plan(int B, int H, int Nq, int Nk) {
   a.tiles = B * H * a.n_qtiles;
   const int nblk = (Nk + ATT_BN - 1) / ATT_BN;
   const int slots = 2 * num_sms();
-  a.full = (a.tiles / slots) * slots;
-  a.tail = a.tiles - a.full;
   a.split = 1;
   a.blocks_per_split = nblk;
+  a.full = a.tiles;
+  a.tail = 0;
+  if (slots <= 0) {  // no device visible (host-side size queries): plan without a split
+    a.workspace_bytes = 0;
+    return a;
+  }
+  a.full = (a.tiles / slots) * slots;
+  a.tail = a.tiles - a.full;
   if (a.tail > 0 && a.tail <= ATT_WS_COUNTERS) {
     int s = 1;
     while (s * 2 <= nblk && a.tail * s * 2 <= slots) s *= 2;
