@@ -245,7 +245,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "stage-2 SDXL UNet + GLV ControlNet denoise step, 4x128x128 latent (1024^2), CFG batch 2, "
                                    "fbcache off, one independent latent per GPU",
-                       "l2": "no explicit flush: 7.7 GB of bf16 weights stream through the 126 MB L2 every step",
+                       "l2": "no explicit flush: 7.7 GB of bf16 weights + 1.5 GB of folded cross-attention operands stream through the 126 MB L2 every step",
                        "cuda_graphs": not args.no_graphs, "tflop_per_step": STEP_TFLOP},
             "e2e": {"value": world * 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e},
