@@ -419,7 +419,9 @@ static AttnPlan attention_plan(int B, int H, int Nq, int Nk) {
   a.tail = a.tiles - a.full;
   if (a.tail > 0 && a.tail <= ATT_WS_COUNTERS) {
     int s = 1;
-    while (s * 2 <= nblk && a.tail * s * 2 <= slots) s *= 2;
+    // at most 4 ranges: a CTA with a single key block spends more on its prologue and the merge than it saves
+    // (N = 1024, 24 tail tiles: 31.7 us split 8 ways, 30.3 us split 4 ways, 32.7 us split 2 ways)
+    while (s * 2 <= nblk && a.tail * s * 2 <= slots && s * 2 <= 4) s *= 2;
     if (s > 1) {
       a.blocks_per_split = (nblk + s - 1) / s;
       a.split = (nblk + a.blocks_per_split - 1) / a.blocks_per_split;  // no empty key ranges

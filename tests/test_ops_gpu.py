@@ -250,7 +250,7 @@ def test_attention_split_is_deterministic_and_leaves_counters_zero(ops):
     """The last partial wave of tiles is split over the key range and merged by the last CTA to arrive:
     repeated calls must agree bit for bit and the arrival counters must be back at zero."""
     from b200sr import ops as _ops
-    B, H, N = 2, 20, 1024  # 320 tiles = 296 + 24 -> the 24 tail tiles are split 8 ways
+    B, H, N = 2, 20, 1024  # 320 tiles = 296 + 24 -> the 24 tail tiles are split over the key range
     C = H * 64
     qkv = _rand(B, N, 3 * C, seed=7).to(bf16)
     outs = [ops.attention(qkv, qkv, qkv, H, q_col=0, k_col=C, v_col=2 * C) for _ in range(4)]
