@@ -164,10 +164,32 @@ int b200sr_sampler_post(const float* eps, const float* x_hat, const float* scala
 int b200sr_euler_from_denoised(const float* denoised, const float* x_hat, const float* scalars, float* x_next,
                                int64_t n, void* stream);
 
-/* Tile blend (sampling.py:753-756, :830-847): acc[win] += tile * weight, cnt[win] += weight; out = acc / cnt. */
+/* Tile blend (sampling.py:753-756, :830-847): acc[win] += tile * weight, cnt[win] += weight; out = acc / cnt.
+ * The product and the sum are rounded separately (no FMA), so a weighted strip formed by
+ * b200sr_tile_weighted_strip on another GPU and added by b200sr_strip_add gives the same bits.  cnt may be
+ * NULL (the weight sum is data independent and can be kept by the caller).                               */
 int b200sr_tile_accumulate(const float* tile, const float* weight, float* acc, float* cnt, int32_t BC, int32_t th,
                            int32_t tw, int32_t H, int32_t W, int32_t h0, int32_t w0, void* stream);
 int b200sr_tile_normalize(const float* acc, const float* cnt, float* out, int64_t n, void* stream);
+
+/* Tile-sharded blend across GPUs (the reference loops over tiles sequentially, sampling.py:727-756): the
+ * part of a window's weighted result that lies inside another rank's window travels as a packed strip.
+ *   strip[bc, y, x] = tile[bc, y0 + y, x0 + x] * weight[y0 + y, x0 + x]       (sender)
+ *   acc[bc, h0 + y, w0 + x] += strip[bc, y, x]                                (owner, in global window order) */
+int b200sr_tile_weighted_strip(const float* tile, const float* weight, float* strip, int32_t BC, int32_t th, int32_t tw,
+                               int32_t y0, int32_t x0, int32_t sh, int32_t sw, void* stream);
+int b200sr_strip_add(const float* strip, float* acc, int32_t BC, int32_t sh, int32_t sw, int32_t H, int32_t W,
+                     int32_t h0, int32_t w0, void* stream);
+
+/* Up to 8 small device-to-device copies in one launch (bytes % 4 == 0, 4-byte aligned): the per-step loader of
+ * the sampler engine (latent, noise, this step's row of the scalar table sampling.py:598-606 and of the
+ * precomputed timestep-embedding projections openaimodel.py:281-287) into the buffers a CUDA graph reads. */
+typedef struct b200sr_copy {
+  const void* src;
+  void* dst;
+  int64_t bytes;
+} b200sr_copy;
+int b200sr_copy_batch(const b200sr_copy* copies, int32_t n, void* stream);
 
 /* First-block-cache similarity (DFBCache.py:98-134): result[0] = mean|prev-cur| / (mean|prev| + 1e-6),
  * result[1] = (result[0] < threshold[0]).  workspace = 2 zeroed doubles (re-zeroed on return). */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SR_LIB selects another in-tree build of the same ABI (A/B kernel experiments); default = the product library
 LIB_PATH = os.path.join(_HERE, os.environ.get("B200SR_LIB", "libb200sr.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_i64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -39,6 +39,12 @@ class Epilogue(C.Structure):
         ("w_rows_per_group", c_int),
         ("w_group_stride", c_i64),
     ]
+
+
+class Copy(C.Structure):
+    """Mirror of ``b200sr_copy``."""
+
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("bytes", c_i64)]
 
 
 P = c_void_p
@@ -76,6 +82,9 @@ SIGNATURES = {
     "b200sr_tile_normalize": (c_int, [P, P, P, c_i64, P]),
     "b200sr_rel_l1_similarity": (c_int, [P, P, c_i64, P, P, P, P]),
     "b200sr_sr3_update": (c_int, [P, P, P, P, P, c_i64, P]),
+    "b200sr_copy_batch": (c_int, [C.POINTER(Copy), c_int, P]),
+    "b200sr_tile_weighted_strip": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200sr_strip_add": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
 }
 
 _ERRORS = {-22: "EINVAL (bad shape / alignment / flags)", -19: "ENODEV (no sm_100 device / driver)", -5: "EIO (CUDA launch error)"}

@@ -102,27 +102,51 @@ def _silu_of(emb: torch.Tensor) -> torch.Tensor:
     return s
 
 
-def _project_emb_for_resblocks(holder: Packed, root: nn.Module, emb: torch.Tensor) -> None:
+class EmbSlot:
+    """Stand-in for the `emb` argument when every ResBlock's projection of it is already known (the engine
+    precomputes them for all sampler steps): only carries the per-block table ``_b200sr_rb``."""
+
+    def __init__(self, table):
+        self._b200sr_rb = table
+
+
+def _resblocks_of(root: nn.Module):
+    blocks = root.__dict__.get("_b200sr_resblocks")
+    if blocks is None:
+        blocks = [m for m in root.modules() if isinstance(m, ResBlock)]
+        root.__dict__["_b200sr_resblocks"] = blocks
+    return blocks
+
+
+def rb_table(root: nn.Module, proj: torch.Tensor):
+    """proj: fp32 [B, sum Cout] (row stride arbitrary) -> {id(ResBlock): its [B, Cout] column window}."""
+    table, off = {}, 0
+    for blk in _resblocks_of(root):
+        table[id(blk)] = proj[:, off:off + blk.out_channels]
+        off += blk.out_channels
+    return table
+
+
+def _project_emb_for_resblocks(holder: Packed, root: nn.Module, emb: torch.Tensor) -> Optional[torch.Tensor]:
     """Every ResBlock applies its own Linear to the same SiLU(emb) (openaimodel.py:281-283, :337-341).
     They only depend on emb, so all of a network's projections run as ONE GEMM against the row-wise
     concatenation of the weights right after emb is known; each block then reads its column window
-    (fp32 [B, sum Cout], consumed through ``ld_rowvec``) instead of launching an M = B GEMM of its own."""
-    blocks = [m for m in root.modules() if isinstance(m, ResBlock)]
+    (fp32 [B, sum Cout], consumed through ``ld_rowvec``) instead of launching an M = B GEMM of its own.
+    Returns the [B, sum Cout] projection (also attached to `emb` as a per-block table)."""
+    blocks = _resblocks_of(root)
     if not blocks:
-        return
+        return None
     params = tuple(p for blk in blocks for p in (blk.emb_layers[1].weight, blk.emb_layers[1].bias))
     w_all, b_all = holder._pk("rb_emb", params, lambda *ps: (
         torch.cat([ops.pack_linear(w) for w in ps[0::2]], 0).contiguous(),
         torch.cat([_F32(b) for b in ps[1::2]], 0).contiguous()))
     proj = ops.gemm(_silu_of(emb), w_all, b_all, out_fp32=True)  # [B, sum Cout]
-    table, off = {}, 0
-    for blk in blocks:
-        table[id(blk)] = proj[:, off:off + blk.out_channels]
-        off += blk.out_channels
     try:
-        emb._b200sr_rb = table
+        emb._b200sr_rb = rb_table(root, proj)
+        emb._b200sr_proj = proj
     except Exception:  # pragma: no cover - exotic tensor subclasses
         pass
+    return proj
 
 
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
@@ -290,17 +314,45 @@ class CrossAttention(nn.Module, Packed):
             qkv = ops.gemm(x, w)
             return ops.attention(qkv, qkv, qkv, self.heads, q_col=0, k_col=inner, v_col=2 * inner, scale=self.scale)
         q = _linear(self, "q", self.to_q, x)
-        bound = self.__dict__.get("_static", {}).get(id(context))
+        bound = self._bound_entry(context)
         if kv is not None:
             pass
-        elif bound is not None and bound[0] is context:
+        elif bound is not None:
             kv = bound[1]  # hoisted by bind_static_context(): the text context is constant over the steps
         else:
             kv = ops.gemm(context, self._wkv())
+        if kv.shape[0] != q.shape[0]:
+            # a context shared by n latents per CFG half ([uncond; cond] captions of a batch of tiles): rows of q are
+            # ordered [uncond x n; cond x n].  Only shapes that miss the folded path get here (tokens % 256 != 0).
+            if q.shape[0] % kv.shape[0]:
+                raise ValueError(f"context batch {kv.shape[0]} does not divide the query batch {q.shape[0]}")
+            kv = kv.repeat_interleave(q.shape[0] // kv.shape[0], dim=0)
         return ops.attention(q, kv, kv, self.heads, q_col=0, k_col=0, v_col=inner, scale=self.scale)
 
     def _wkv(self):
         return self._pk("kv", (self.to_k.weight, self.to_v.weight), lambda k, v: torch.cat([k, v], 0).to(bf16).contiguous())
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in (self.to_q.weight, self.to_k.weight, self.to_v.weight,
+                                                          self.to_out[0].weight))
+
+    def _bound_entry(self, context):
+        """The (context, kv, folded, weights_key) entry bound for this very tensor object, or None.  An entry made
+        from projection weights that have changed since (load_state_dict, .to()) is re-bound on the spot."""
+        if context is None:
+            return None
+        table = self.__dict__.get("_static")
+        if not table:
+            return None
+        e = table.get(id(context))
+        if e is None or e[0] is not context:
+            return None
+        if e[3] != self._weights_key():
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("cross-attention weights changed after bind_static_context(); re-bind before capture")
+            self.bind_static_context(context)
+            e = table[id(context)]
+        return e
 
     def bind_static_context(self, context: Optional[torch.Tensor]) -> None:
         """Precompute K/V of a context that stays constant across sampler steps (the text embedding:
@@ -321,7 +373,15 @@ class CrossAttention(nn.Module, Packed):
             for dst, src in zip(old[2], fused):
                 dst.copy_(src)
             fused = old[2]
-        table[id(context)] = (context, kv, fused)
+        table[id(context)] = (context, kv, fused, self._weights_key())
+
+    def bound_tensors(self, context):
+        """The device tensors bound for `context` (K/V, folded K', folded V'): snapshot / restore by the engine
+        when it switches between captions."""
+        e = self.__dict__.get("_static", {}).get(id(context))
+        if e is None or e[0] is not context:
+            return []
+        return [e[1]] + ([e[2][0], e[2][1]] if e[2] is not None else [])
 
     SEG = 80  # key slots per head in the folded form (77 text tokens, padded)
 
@@ -356,12 +416,16 @@ class CrossAttention(nn.Module, Packed):
         x = tokens_bf16(x)
         ctx = tokens_bf16(context) if context is not None else None
         if ctx is not None and kv is None and x.dim() == 3 and x.shape[1] % 256 == 0:
-            bound = self.__dict__.get("_static", {}).get(id(ctx))
-            if bound is not None and bound[0] is ctx and bound[2] is not None and bound[2][0].shape[0] == x.shape[0]:
+            bound = self._bound_entry(ctx)
+            if bound is not None and bound[2] is not None and x.shape[0] % bound[2][0].shape[0] == 0:
+                # The bound context may have fewer rows than x: [uncond; cond] captions shared by several latents
+                # (tiles of one image batched into one step).  Rows of x are ordered [uncond x n; cond x n], so
+                # each context row serves a contiguous block of n * T query rows.
                 k_fold, v_fold, tk = bound[2]
-                p = ops.gemm(x, k_fold, softmax_valid=int(tk), w_rows_per_group=x.shape[1])
+                rpg = x.shape[1] * (x.shape[0] // k_fold.shape[0])
+                p = ops.gemm(x, k_fold, softmax_valid=int(tk), w_rows_per_group=rpg)
                 bias = self._pk("out.b", (self.to_out[0].bias,), _F32)
-                return ops.gemm(p, v_fold, bias, residual=residual, alpha=alpha, w_rows_per_group=x.shape[1])
+                return ops.gemm(p, v_fold, bias, residual=residual, alpha=alpha, w_rows_per_group=rpg)
         return _linear(self, "out", self.to_out[0], self.attend(x, ctx, kv), residual=residual, alpha=alpha)
 
 
@@ -702,8 +766,9 @@ class GLVControl(UNetModel):
         self.input_hint_block = TimestepEmbedSequential(
             zero_module(nn.Conv2d(self.in_channels, self.model_channels, 3, padding=1)))
 
-    def forward_nhwc(self, x, timesteps, xt, context, y) -> List[torch.Tensor]:
-        emb = self._embed(timesteps, y)
+    def forward_nhwc(self, x, timesteps, xt, context, y, emb=None) -> List[torch.Tensor]:
+        if emb is None:
+            emb = self._embed(timesteps, y)
         hint = _stem_conv(self.input_hint_block[0], x)
         hs = []
         h = _stem_conv(self.input_blocks[0][0], xt, addend=hint)  # h = conv(xt); h += guided_hint
@@ -890,6 +955,15 @@ def bind_text_context(wrapper: nn.Module, context: Optional[torch.Tensor]) -> in
             m.attn2.bind_static_context(context)
             n += 1
     return n
+
+
+def text_binding_tensors(wrapper: nn.Module, context: torch.Tensor) -> List[torch.Tensor]:
+    """All tensors bind_text_context(wrapper, context) produced, in module order."""
+    out = []
+    for m in wrapper.modules():
+        if isinstance(m, BasicTransformerBlock) and not m.disable_self_attn:
+            out.extend(m.attn2.bound_tensors(context))
+    return out
 
 
 def build_stage2(network_params: Dict, control_params: Dict) -> ControlWrapper:

@@ -68,6 +68,11 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise _lib.B200SRError(f"{name}: expected a CUDA tensor (b200sr has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the *current* device's current stream: one process drives one GPU, or the
+        # caller selects the device (torch.cuda.device / set_device) around the call
+        raise _lib.B200SRError(f"{name}: tensor lives on {t.device} but the current CUDA device is "
+                               f"{torch.cuda.current_device()}; wrap the call in torch.cuda.device(tensor.device)")
     if t.dtype != dtype:
         raise _lib.B200SRError(f"{name}: expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -75,6 +80,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 
 _ws_cache: dict = {}
+_ws_retired: list = []  # outgrown scratch buffers: never freed, captured CUDA graphs may still hold their addresses
 _ws_slot = [0]  # scratch buffers are per (device, slot): work issued concurrently on a second stream uses slot 1
 
 
@@ -95,13 +101,19 @@ class workspace_slot:
 
 def _workspace(device: torch.device, nbytes: int, kind: str = "gn") -> torch.Tensor:
     """Zero-initialised scratch per (device, stream slot, kernel family); the kernels keep their arrival
-    counters at its start zeroed between launches, so it is reused by every call of that family."""
+    counters at its start zeroed between launches, so it is reused by every call of that family.
+    A buffer that has been handed out is never freed: a CUDA graph captured earlier (by this or another
+    engine) has its address baked in and would otherwise write into recycled memory on replay.  An outgrown
+    buffer is parked in ``_ws_retired``; sizes grow geometrically (floor 16 MB), so there are few of those."""
     key = (device.type, device.index, _ws_slot[0], kind)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() * 4 < nbytes:
-        if torch.cuda.is_current_stream_capturing() and ws is not None:
-            raise _lib.B200SRError("workspace growth during CUDA-graph capture; run one eager warm-up step first")
-        ws = torch.zeros(max(nbytes // 4 + 1, 1 << 18), dtype=torch.float32, device=device)
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.B200SRError("workspace allocation during CUDA-graph capture; run one eager warm-up step first")
+        if ws is not None:
+            _ws_retired.append(ws)
+        floats = max(nbytes // 4 + 1, 1 << 22, 0 if ws is None else 2 * ws.numel())
+        ws = torch.zeros(floats, dtype=torch.float32, device=device)
         _ws_cache[key] = ws
     return ws
 
@@ -489,11 +501,47 @@ def euler_from_denoised(denoised: torch.Tensor, x_hat: torch.Tensor, scalars: to
     return x_next
 
 
-def tile_accumulate(tile: torch.Tensor, weight: torch.Tensor, acc: torch.Tensor, cnt: torch.Tensor, h0: int, w0: int):
+def tile_accumulate(tile: torch.Tensor, weight: torch.Tensor, acc: torch.Tensor, cnt: Optional[torch.Tensor], h0: int,
+                    w0: int):
+    """acc[win] += tile * weight (product and sum rounded separately); cnt[win] += weight unless cnt is None."""
     b, c, th, tw = tile.shape
     H, W = acc.shape[-2:]
-    check(_lib.load().b200sr_tile_accumulate(tile.data_ptr(), weight.data_ptr(), acc.data_ptr(), cnt.data_ptr(), b * c,
+    check(_lib.load().b200sr_tile_accumulate(tile.data_ptr(), weight.data_ptr(), acc.data_ptr(), _ptr(cnt), b * c,
                                              th, tw, H, W, h0, w0, _stream()), "tile_accumulate")
+
+
+def tile_weighted_strip(tile: torch.Tensor, weight: torch.Tensor, y0: int, x0: int, sh: int, sw: int,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(tile * weight)[:, :, y0:y0+sh, x0:x0+sw] packed contiguously (fp32): what a peer rank's overlapping window needs."""
+    _req(tile, torch.float32, "tile_weighted_strip.tile")
+    b, c, th, tw = tile.shape
+    if out is None:
+        out = torch.empty(b, c, sh, sw, dtype=torch.float32, device=tile.device)
+    check(_lib.load().b200sr_tile_weighted_strip(tile.data_ptr(), weight.data_ptr(), out.data_ptr(), b * c, th, tw, y0, x0,
+                                                 sh, sw, _stream()), "tile_weighted_strip")
+    return out
+
+
+def strip_add(strip: torch.Tensor, acc: torch.Tensor, h0: int, w0: int) -> None:
+    """acc[:, :, h0:h0+sh, w0:w0+sw] += strip (fp32, contiguous strip [B, C, sh, sw])."""
+    _req(strip, torch.float32, "strip_add.strip")
+    b, c, sh, sw = strip.shape
+    H, W = acc.shape[-2:]
+    check(_lib.load().b200sr_strip_add(strip.data_ptr(), acc.data_ptr(), b * c, sh, sw, H, W, h0, w0, _stream()),
+          "strip_add")
+
+
+def copy_batch(pairs) -> None:
+    """Up to 8 (dst, src) copies between contiguous device tensors of equal byte size in ONE kernel launch."""
+    n = len(pairs)
+    arr = (_lib.Copy * n)()
+    for i, (dst, src) in enumerate(pairs):
+        nb = src.numel() * src.element_size()
+        if not (dst.is_cuda and src.is_cuda and dst.is_contiguous() and src.is_contiguous()) or \
+                dst.numel() * dst.element_size() != nb:
+            raise _lib.B200SRError("copy_batch: contiguous CUDA tensors of equal byte size expected")
+        arr[i].src, arr[i].dst, arr[i].bytes = src.data_ptr(), dst.data_ptr(), nb
+    check(_lib.load().b200sr_copy_batch(arr, n, _stream()), "copy_batch")
 
 
 def tile_normalize(acc: torch.Tensor, cnt: torch.Tensor) -> torch.Tensor:

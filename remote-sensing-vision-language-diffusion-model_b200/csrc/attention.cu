@@ -483,12 +483,11 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
   p.trace = g_att_trace;
 #endif
   const size_t smem_bytes = ATT_TILE_BYTES * (1 + 2 * ATT_STAGES) + 1024 + 128 + 2048;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // per device
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem_bytes)) != cudaSuccess)
       return B200SR_ELAUNCH;
-    attr_set = true;
   }
   dim3 grid(plan.full + plan.tail * plan.split);
   return launch_k(attention_d64_kernel, grid, dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmK, tmV, p) == cudaSuccess

@@ -42,6 +42,14 @@ int num_sms() {
   return cached[dev];
 }
 
+bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -108,6 +116,10 @@ int rel_l1_similarity(const void* prev, const void* cur, long long n, const floa
                       float* result, cudaStream_t stream);
 int sr3_update(const float* x, const float* eps, const float* noise, const float* scalars, float* out, long long n,
                cudaStream_t stream);
+int copy_batch(const void* const* src, void* const* dst, const long long* bytes, int n, cudaStream_t stream);
+int tile_weighted_strip(const float* tile, const float* weight, float* strip, int BC, int th, int tw, int y0, int x0,
+                        int sh, int sw, cudaStream_t stream);
+int strip_add(const float* strip, float* acc, int BC, int sh, int sw, int H, int W, int h0, int w0, cudaStream_t stream);
 
 static EpilogueArgs to_args(const b200sr_epilogue* e) {
   EpilogueArgs a;
@@ -137,7 +149,7 @@ using namespace b200sr;
 
 extern "C" {
 
-int b200sr_abi_version(void) { return 2; }
+int b200sr_abi_version(void) { return 3; }
 int b200sr_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200SR_ENODEV;
@@ -242,7 +254,7 @@ int b200sr_euler_from_denoised(const float* denoised, const float* x_hat, const 
 }
 int b200sr_tile_accumulate(const float* tile, const float* weight, float* acc, float* cnt, int32_t BC, int32_t th,
                            int32_t tw, int32_t H, int32_t W, int32_t h0, int32_t w0, void* stream) {
-  if (tile == nullptr || weight == nullptr || acc == nullptr || cnt == nullptr) return B200SR_EINVAL;
+  if (tile == nullptr || weight == nullptr || acc == nullptr) return B200SR_EINVAL;  // cnt may be NULL
   return tile_accumulate(tile, weight, acc, cnt, BC, th, tw, H, W, h0, w0, S(stream));
 }
 int b200sr_tile_normalize(const float* acc, const float* cnt, float* out, int64_t n, void* stream) {
@@ -259,6 +271,29 @@ int b200sr_sr3_update(const float* x, const float* eps, const float* noise, cons
                       int64_t n, void* stream) {
   if (x == nullptr || eps == nullptr || scalars == nullptr || out == nullptr) return B200SR_EINVAL;
   return sr3_update(x, eps, noise, scalars, out, n, S(stream));
+}
+
+int b200sr_copy_batch(const b200sr_copy* copies, int32_t n, void* stream) {
+  if (copies == nullptr || n <= 0 || n > B200SR_MAX_COPIES) return B200SR_EINVAL;
+  const void* src[B200SR_MAX_COPIES];
+  void* dst[B200SR_MAX_COPIES];
+  long long bytes[B200SR_MAX_COPIES];
+  for (int i = 0; i < n; ++i) {
+    src[i] = copies[i].src;
+    dst[i] = copies[i].dst;
+    bytes[i] = copies[i].bytes;
+  }
+  return copy_batch(src, dst, bytes, n, S(stream));
+}
+int b200sr_tile_weighted_strip(const float* tile, const float* weight, float* strip, int32_t BC, int32_t th, int32_t tw,
+                               int32_t y0, int32_t x0, int32_t sh, int32_t sw, void* stream) {
+  if (tile == nullptr || weight == nullptr || strip == nullptr) return B200SR_EINVAL;
+  return tile_weighted_strip(tile, weight, strip, BC, th, tw, y0, x0, sh, sw, S(stream));
+}
+int b200sr_strip_add(const float* strip, float* acc, int32_t BC, int32_t sh, int32_t sw, int32_t H, int32_t W,
+                     int32_t h0, int32_t w0, void* stream) {
+  if (strip == nullptr || acc == nullptr) return B200SR_EINVAL;
+  return strip_add(strip, acc, BC, sh, sw, H, W, h0, w0, S(stream));
 }
 
 }  // extern "C"

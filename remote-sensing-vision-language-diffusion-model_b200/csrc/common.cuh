@@ -11,6 +11,8 @@
 #define B200SR_HANG_GUARD 1  // trap instead of spinning forever on a lost mbarrier phase
 #endif
 
+#define B200SR_MAX_COPIES 8  // b200sr_copy_batch: copies per launch
+
 namespace b200sr {
 
 // ------------------------------------------------------------------------------------------
@@ -298,6 +300,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
+// true the first time it is called for (flags, current device): per-device one-time setup such as
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-device attribute
+bool first_use_on_device(bool (&flags)[64]);
 bool pdl_enabled();  // B200SR_PDL=0 disables programmatic dependent launch (debugging)
 
 // Launch with the PDL attribute (and an optional cluster size along x).

@@ -380,11 +380,9 @@ int conv3x3_small(const void* x, const void* w, const float* bias, const void* a
     if (out_nchw_f32) return B200SR_EINVAL;
     const size_t smem = static_cast<size_t>(Cout) * 9 * Cin * sizeof(float);
     if (smem > 96 * 1024) return B200SR_EINVAL;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the attribute is per device
+    if (first_use_on_device(attr_set))
       cudaFuncSetAttribute(conv3x3_few_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_set = true;
-    }
     const size_t total = static_cast<size_t>(N) * H * W * (Cout / 8);
     int grid = static_cast<int>((total + 255) / 256);
     if (grid > num_sms() * 4) grid = num_sms() * 4;
@@ -526,8 +524,10 @@ __global__ void tile_accumulate_kernel(const float* __restrict__ tile, const flo
     const size_t bc = i / (static_cast<size_t>(tw) * th);
     const float wgt = weight[y * tw + x];
     const size_t o = (bc * H + (h0 + y)) * W + (w0 + x);
-    acc[o] += tile[i] * wgt;
-    cnt[o] += wgt;
+    // explicit round-to-nearest multiply then add (no FMA contraction): a rank that ships the weighted strip
+    // tile * w to the window's owner, which adds it, must produce the same bits as this local accumulation
+    acc[o] = __fadd_rn(acc[o], __fmul_rn(tile[i], wgt));
+    if (cnt != nullptr) cnt[o] += wgt;
   }
 }
 __global__ void tile_normalize_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
@@ -649,6 +649,105 @@ int sr3_update(const float* x, const float* eps, const float* noise, const float
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   launch_k(sr3_update_kernel, dim3(grid), dim3(256), 0, stream, 1, x, eps, noise, scalars, out, static_cast<size_t>(n));
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched small device-to-device copies in ONE launch (per-step loader of the sampler engine: latent, noise,
+// the step's row of the scalar table and of the precomputed embedding projections -> the static buffers a
+// captured CUDA graph reads).  Each copy is 4-byte granular; 16-byte vectors when both ends allow it.
+// ------------------------------------------------------------------------------------------
+struct CopyBatchArgs {
+  const void* src[B200SR_MAX_COPIES];
+  void* dst[B200SR_MAX_COPIES];
+  long long bytes[B200SR_MAX_COPIES];
+};
+__global__ void copy_batch_kernel(const CopyBatchArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int k = blockIdx.y;
+  const long long nbytes = a.bytes[k];
+  const uintptr_t s = reinterpret_cast<uintptr_t>(a.src[k]), d = reinterpret_cast<uintptr_t>(a.dst[k]);
+  const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t nth = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (((s | d | static_cast<uintptr_t>(nbytes)) & 15) == 0) {
+    const uint4* sp = reinterpret_cast<const uint4*>(s);
+    uint4* dp = reinterpret_cast<uint4*>(d);
+    for (size_t i = tid; i < static_cast<size_t>(nbytes >> 4); i += nth) dp[i] = sp[i];
+  } else {
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(s);
+    uint32_t* dp = reinterpret_cast<uint32_t*>(d);
+    for (size_t i = tid; i < static_cast<size_t>(nbytes >> 2); i += nth) dp[i] = sp[i];
+  }
+}
+int copy_batch(const void* const* src, void* const* dst, const long long* bytes, int n, cudaStream_t stream) {
+  if (n <= 0 || n > B200SR_MAX_COPIES) return B200SR_EINVAL;
+  CopyBatchArgs a;
+  long long mx = 0;
+  for (int i = 0; i < n; ++i) {
+    if (src[i] == nullptr || dst[i] == nullptr || bytes[i] <= 0 || (bytes[i] & 3) ||
+        (reinterpret_cast<uintptr_t>(src[i]) & 3) || (reinterpret_cast<uintptr_t>(dst[i]) & 3))
+      return B200SR_EINVAL;
+    a.src[i] = src[i];
+    a.dst[i] = dst[i];
+    a.bytes[i] = bytes[i];
+    if (bytes[i] > mx) mx = bytes[i];
+  }
+  int gx = static_cast<int>((mx / 16 + 255) / 256);
+  if (gx < 1) gx = 1;
+  if (gx > num_sms() * 4) gx = num_sms() * 4;
+  launch_k(copy_batch_kernel, dim3(gx, n), dim3(256), 0, stream, 1, a);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tile-sharded blend, halo side (sampling.py:753-756 across GPUs): strip = tile[:, y0:y0+sh, x0:x0+sw] * weight
+// (the same round-to-nearest product tile_accumulate forms), packed contiguously for the peer that owns an
+// overlapping window; and acc[:, h0:h0+sh, w0:w0+sw] += strip on the receiving side.
+// ------------------------------------------------------------------------------------------
+__global__ void tile_weighted_strip_kernel(const float* __restrict__ tile, const float* __restrict__ weight,
+                                           float* __restrict__ strip, int BC, int th, int tw, int y0, int x0, int sh,
+                                           int sw) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t total = static_cast<size_t>(BC) * sh * sw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % sw);
+    const int y = static_cast<int>((i / sw) % sh);
+    const size_t bc = i / (static_cast<size_t>(sw) * sh);
+    strip[i] = __fmul_rn(tile[(bc * th + (y0 + y)) * tw + (x0 + x)], weight[(y0 + y) * tw + (x0 + x)]);
+  }
+}
+__global__ void strip_add_kernel(const float* __restrict__ strip, float* __restrict__ acc, int BC, int sh, int sw, int H,
+                                 int W, int h0, int w0) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t total = static_cast<size_t>(BC) * sh * sw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % sw);
+    const int y = static_cast<int>((i / sw) % sh);
+    const size_t bc = i / (static_cast<size_t>(sw) * sh);
+    const size_t o = (bc * H + (h0 + y)) * W + (w0 + x);
+    acc[o] = __fadd_rn(acc[o], strip[i]);
+  }
+}
+int tile_weighted_strip(const float* tile, const float* weight, float* strip, int BC, int th, int tw, int y0, int x0,
+                        int sh, int sw, cudaStream_t stream) {
+  if (BC <= 0 || sh <= 0 || sw <= 0 || y0 < 0 || x0 < 0 || y0 + sh > th || x0 + sw > tw) return B200SR_EINVAL;
+  const size_t total = static_cast<size_t>(BC) * sh * sw;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  launch_k(tile_weighted_strip_kernel, dim3(grid), dim3(256), 0, stream, 1, tile, weight, strip, BC, th, tw, y0, x0, sh, sw);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+int strip_add(const float* strip, float* acc, int BC, int sh, int sw, int H, int W, int h0, int w0, cudaStream_t stream) {
+  if (BC <= 0 || sh <= 0 || sw <= 0 || h0 < 0 || w0 < 0 || h0 + sh > H || w0 + sw > W) return B200SR_EINVAL;
+  const size_t total = static_cast<size_t>(BC) * sh * sw;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  launch_k(strip_add_kernel, dim3(grid), dim3(256), 0, stream, 1, strip, acc, BC, sh, sw, H, W, h0, w0);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

@@ -847,12 +847,11 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
 #ifdef B200SR_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // per device (and per kCluster instantiation)
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
       return B200SR_ELAUNCH;
-    attr_set = true;
   }
   const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
   const int slots = num_sms() / kCluster;

@@ -193,7 +193,26 @@ def euler_from_denoised(denoised, x_hat, scalars):
 def tile_accumulate(tile, weight, acc, cnt, h0, w0):
     th, tw = tile.shape[-2:]
     acc[:, :, h0:h0 + th, w0:w0 + tw] += tile * weight
-    cnt[:, :, h0:h0 + th, w0:w0 + tw] += weight
+    if cnt is not None:
+        cnt[:, :, h0:h0 + th, w0:w0 + tw] += weight
+
+
+def tile_weighted_strip(tile, weight, y0, x0, sh, sw, out=None):
+    r = (tile * weight)[:, :, y0:y0 + sh, x0:x0 + sw].contiguous()
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def strip_add(strip, acc, h0, w0):
+    sh, sw = strip.shape[-2:]
+    acc[:, :, h0:h0 + sh, w0:w0 + sw] += strip
+
+
+def copy_batch(pairs):
+    for dst, src in pairs:
+        dst.view(-1).view(torch.uint8).copy_(src.view(-1).view(torch.uint8))
 
 
 def tile_normalize(acc, cnt):
