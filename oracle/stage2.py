@@ -80,6 +80,12 @@ def resblock(sd: SD, p: str, x: torch.Tensor, emb: torch.Tensor) -> torch.Tensor
     return x + h
 
 
+# "manual" = softmax(q k^T / 8) v spelled out (what the golden vectors were pinned with); "sdpa" = the call the reference
+# itself makes without xformers, F.scaled_dot_product_attention (attention.py:275-277) — selected by bench.py's
+# GPU eager baseline so that stock torch runs its fused attention kernel instead of materialising the score matrix.
+ATTENTION = "manual"
+
+
 def cross_attention(sd: SD, p: str, x: torch.Tensor, context: Optional[torch.Tensor]) -> torch.Tensor:
     """CrossAttention.forward, heads of 64, scale 1/8 — sgm/modules/attention.py:222-285."""
     ctx = x if context is None else context
@@ -89,8 +95,11 @@ def cross_attention(sd: SD, p: str, x: torch.Tensor, context: Optional[torch.Ten
     b, n, c = q.shape
     h = c // 64
     q, k, v = (t.reshape(b, -1, h, 64).transpose(1, 2) for t in (q, k, v))
-    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
-    o = (att @ v).transpose(1, 2).reshape(b, n, c)
+    if ATTENTION == "sdpa":
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+    else:
+        att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(b, n, c)
     return _linear(sd, p + "to_out.0.", o)
 
 
@@ -231,3 +240,25 @@ def control_wrapper(sd: SD, x, t, c: dict, control_scale: float = 1.0, model_cha
     control = glv_control(sd, "control_model.", c["control"], t, x, c["crossattn"], c["vector"], model_channels)
     h, hs, emb = unet_input_stage(sd, "diffusion_model.", x, t, c["crossattn"], c["vector"], model_channels)
     return unet_output_stage(sd, "diffusion_model.", h, hs, emb, c["crossattn"], control, control_scale).float()
+
+
+def network(sd: SD):
+    """The callable DiscreteDenoiserWithControl hands its arguments to (denoiser.py:76-78): ControlWrapper.forward
+    for fbcache_mode "none" / "input_stage1" / "input_stage2" (wrappers.py:84-110, SR_modules.py:660-730).  The
+    control features computed in stage 1 are carried in partial_info, as the reference does (SR_modules.py:694)."""
+
+    def net(x, t, c, control_scale=1.0, fbcache_mode="none", partial_info=None):
+        with torch.no_grad():
+            if fbcache_mode == "none":
+                return control_wrapper(sd, x, t, c, control_scale)
+            if fbcache_mode == "input_stage1":
+                control = glv_control(sd, "control_model.", c["control"], t, x, c["crossattn"], c["vector"])
+                h, hs, emb = unet_input_stage(sd, "diffusion_model.", x, t, c["crossattn"], c["vector"])
+                return {"mode": "input", "h": h, "hs": hs, "emb": emb, "context": c["crossattn"], "control": control}
+            if fbcache_mode == "input_stage2":
+                p = partial_info
+                return unet_output_stage(sd, "diffusion_model.", p["h"], p["hs"], p["emb"], p["context"], p["control"],
+                                         control_scale).float()
+        raise ValueError(fbcache_mode)
+
+    return net

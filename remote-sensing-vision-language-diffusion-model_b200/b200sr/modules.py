@@ -957,6 +957,17 @@ def bind_text_context(wrapper: nn.Module, context: Optional[torch.Tensor]) -> in
     return n
 
 
+def unbind_text_context(wrapper: nn.Module, context: torch.Tensor) -> None:
+    """Drop what bind_text_context(wrapper, context) stored for this one context tensor (an engine going away)."""
+    for m in wrapper.modules():
+        if isinstance(m, BasicTransformerBlock) and not m.disable_self_attn:
+            table = m.attn2.__dict__.get("_static")
+            if table:
+                e = table.get(id(context))
+                if e is not None and e[0] is context:
+                    del table[id(context)]
+
+
 def text_binding_tensors(wrapper: nn.Module, context: torch.Tensor) -> List[torch.Tensor]:
     """All tensors bind_text_context(wrapper, context) produced, in module order."""
     out = []

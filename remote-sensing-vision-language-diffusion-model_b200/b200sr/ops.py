@@ -28,9 +28,10 @@ def launch_count() -> int:
     return _lib.LAUNCHES[0]
 
 
-# Optional per-launch timing of the dense kernels (bench.py roofline leg): when a list is installed,
-# every gemm / conv3x3 / attention launch is bracketed by CUDA events on the launching stream and
-# appended as (kind, algorithmic_flops, start_event, end_event).
+# Optional per-launch timing (bench.py roofline leg): when a list is installed, every gemm / conv3x3 / attention /
+# group_norm / layer_norm launch is bracketed by CUDA events on the launching stream and appended as
+# (kind, algorithmic work, start_event, end_event, description); work = FLOPs for the dense kernels and
+# algorithmic bytes (each operand read once, the result written once, bf16) for the normalisation kernels.
 _profile = None
 
 
@@ -317,10 +318,12 @@ def group_norm(
     lib = _lib.load()
     ws = _workspace(x.device, lib.b200sr_group_norm_workspace_bytes(n, hw, c, groups))
     y = torch.empty_like(x)
-    rc = lib.b200sr_group_norm_nhwc(
-        x.data_ptr(), y.data_ptr(), _ptr(weight), _ptr(bias), n, hw, c, groups, eps, int(silu), _ptr(sft_gamma),
-        _ptr(sft_beta), _ptr(raw), float(control_scale), ws.data_ptr(), _stream()
-    )
+    nbytes = 2.0 * x.numel() * (2 + (2 if sft_gamma is not None else 0) + (1 if raw is not None and control_scale != 1.0 else 0))
+    with _Timed("group_norm", nbytes, f"N{n} HW{hw} C{c}{' sft' if sft_gamma is not None else ''}"):
+        rc = lib.b200sr_group_norm_nhwc(
+            x.data_ptr(), y.data_ptr(), _ptr(weight), _ptr(bias), n, hw, c, groups, eps, int(silu), _ptr(sft_gamma),
+            _ptr(sft_beta), _ptr(raw), float(control_scale), ws.data_ptr(), _stream()
+        )
     check(rc, f"group_norm N={n} HW={hw} C={c}", kernels=2)
     return y
 
@@ -330,7 +333,8 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
     c = x.shape[-1]
     m = x.numel() // c
     y = torch.empty_like(x)
-    rc = _lib.load().b200sr_layer_norm(x.data_ptr(), y.data_ptr(), weight.data_ptr(), bias.data_ptr(), m, c, eps, _stream())
+    with _Timed("layer_norm", 4.0 * x.numel(), f"M{m} C{c}"):
+        rc = _lib.load().b200sr_layer_norm(x.data_ptr(), y.data_ptr(), weight.data_ptr(), bias.data_ptr(), m, c, eps, _stream())
     check(rc, f"layer_norm M={m} C={c}")
     return y
 

@@ -262,6 +262,22 @@ class Stage2Engine:
         for i in range(0, len(pairs), 8):
             ops.copy_batch(pairs[i:i + 8])
 
+    def close(self) -> None:
+        """Release what this engine stored on the shared modules (text bindings keyed by its context buffers),
+        its graphs and snapshots.  Engines are cheap to create; the weights stay with the wrapper."""
+        if self.cond is not None and hasattr(self.wrapper, "modules"):
+            from .modules import unbind_text_context
+
+            unbind_text_context(self.wrapper, self.cond["crossattn"])
+            for ch in getattr(self, "cond_half", []) or []:
+                unbind_text_context(self.wrapper, ch["crossattn"])
+        self._graphs.clear()
+        self._static.clear()
+        self._captions.clear()
+        self._emb = None
+        self.cond = None
+        self._caption_src = None
+
     def reset_cache(self):
         self._prev_valid = False
         self._final_valid = False

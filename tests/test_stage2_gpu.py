@@ -188,3 +188,118 @@ def test_full_model_eps_1024(full):
     err_b = rel_l2(eps_b, ref)
     print(f"full-model eps rel-L2 vs fp32 oracle, text context bound (folded cross-attention): {err_b:.4e}")
     assert err_b < 1e-2
+
+
+def _oracle_on_gpu(model):
+    from oracle import sampler as osampler, stage2 as ostage2
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    oden = osampler.Denoiser(device="cuda")
+    net = ostage2.network(sd)
+    return (lambda *a: oden(net, *a)), osampler.RestoreSampler(device="cuda")
+
+
+def test_config3_full_trajectory_psnr(full):
+    """BASELINE config 3, stage 2: 50 RestoreEDMSampler steps of the FULL-depth model on a 128^2 latent with the
+    first-block cache (img_threshold 0.3, dec 1), CUDA graphs, vs the fp32 oracle run on the same GPU with the
+    same noises.  Gate: identical hit/miss trace and final latent PSNR >= 40 dB.
+    A trace that diverges at a near-tie of the similarity test (|diff - thr| within the bf16 error of diff) is
+    reported as such — xfail with the step and margin — not silently passed; any other divergence fails."""
+    from b200sr.sampling import Stage2Engine
+    from oracle import sampler as osampler
+
+    x, c, uc, _ = _cond(128)
+    steps, threshold = 50, 0.3
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    z0 = torch.randn(1, 4, 128, 128, generator=g, device="cuda")
+    noises = [torch.randn(1, 4, 128, 128, generator=g, device="cuda") for _ in range(steps)]
+    den, smp = _oracle_on_gpu(full)
+    zo, s_in, sig = smp.init_loop(z0.clone())
+    thr, cache = threshold, osampler.CacheState()
+    with torch.no_grad():
+        for i in range(steps):
+            zo, thr = smp.step(zo, i, s_in, sig, den, c, uc, 1.0, thr, cache, noises[i])
+    eng = Stage2Engine(full)
+    eng.set_condition(c, uc)
+    z = eng.sample(z0, noises, threshold=threshold, dec=1.0)
+    ours, ref = [t[0] for t in eng.trace], [t[0] for t in smp.trace]
+    print("oracle trace:", "".join("H" if t == "hit" else "m" for t in ref), " misses", ref.count("miss"))
+    print("b200sr trace:", "".join("H" if t == "hit" else "m" for t in ours), " misses", ours.count("miss"))
+    if ours != ref:
+        k = next(i for i, (a, b) in enumerate(zip(ours, ref)) if a != b)
+        d_o, d_r = eng.trace[k][1], smp.trace[k][1]
+        thr_k = next((t[1] for t in reversed(smp.trace[:k]) if t[0] == "miss"), threshold)
+        margin = abs(d_r - thr_k) / max(thr_k, 1e-12)
+        msg = (f"hit/miss traces diverge at step {k}: oracle diff {d_r:.6f}, b200sr diff {d_o:.6f}, threshold {thr_k:.6f} "
+               f"(relative margin {margin:.3e})")
+        assert margin < 2e-2, msg + " — not a near-tie"
+        pytest.xfail(msg + " — near-tie of the similarity test; trajectories are not comparable beyond it")
+    assert [t[1] for t in eng.trace] == pytest.approx([t[1] for t in smp.trace], rel=1e-1)
+    p = psnr(z, zo)
+    print(f"50-step latent PSNR vs fp32 oracle: {p:.2f} dB, rel-L2 {rel_l2(z, zo):.3e}")
+    assert p >= 40.0
+
+
+def test_tiled_step_vs_oracle(full):
+    """BASELINE config 4 on one GPU: one tiled sampler step (sampling.py:716-756 with SURVEY section 5 semantics) on
+    a 256^2 latent (9 windows of 128^2, stride 96) vs the fp32 oracle's tiled step; also with three windows per
+    network call (shared caption), and through the rank-sharded stepper (world 1)."""
+    from b200sr import ops
+    from b200sr.parallel import EngineTileRunner, PooledTileStepper
+    from b200sr.sampling import Stage2Engine
+    from oracle import sampler as osampler
+
+    L = 256
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randn(1, 4, L, L, generator=g, device="cuda") * (1 + 14.6146**2) ** 0.5
+    lq = torch.randn(1, 4, L, L, generator=g, device="cuda")
+    noise = torch.randn(1, 4, L, L, generator=g, device="cuda")
+    _, c, uc, _ = _cond(128)
+    c = {k: v for k, v in c.items() if k != "control"}
+    uc = {k: v for k, v in uc.items() if k != "control"}
+    den, smp = _oracle_on_gpu(full)
+    _, s_in, sig = smp.init_loop(x.clone())
+    i = 3
+    with torch.no_grad():
+        ref = osampler.tiled_step(smp, x, i, s_in, sig, den, dict(c, control=lq), dict(uc, control=lq), 128, 96, noise)
+    eng = Stage2Engine(full)
+    out1 = eng.tiled_step(x, i, noise, lq, c, uc, 128, 96)
+    print(f"tiled step rel-L2 of the update vs oracle: {rel_l2(out1 - x, ref - x):.3e}, PSNR {psnr(out1, ref):.1f} dB")
+    assert rel_l2(out1 - x, ref - x) < 1e-2 and psnr(out1, ref) >= 40.0
+    out3 = Stage2Engine(full).tiled_step(x, i, noise, lq, c, uc, 128, 96, tile_batch=3)
+    assert rel_l2(out3 - x, ref - x) < 1e-2 and rel_l2(out3 - x, out1 - x) < 5e-3
+    # the sharded stepper with world size 1 is the same computation: bit-identical to tiled_step
+    st = PooledTileStepper(1, L, L, 128, 96, device="cuda", blend=ops)
+    runner = EngineTileRunner(lambda: Stage2Engine(full), {0: (c, uc)}, {0: lq})
+    out_s = st.step({0: x}, i, {0: noise}, runner)[0]
+    assert torch.equal(out_s, out1)
+
+
+def test_engine_batch_of_latents(small):
+    """Two latents per step (CFG batch 4) == the latents run alone, within bf16 noise; the step loader's
+    precomputed embedding rows == the per-step embedding path."""
+    from b200sr.sampling import Stage2Engine
+    from oracle import inputs
+
+    xa, ca, uca = inputs.stage2_inputs(latent=32, seed=21)
+    xb, cb, ucb = inputs.stage2_inputs(latent=32, seed=22)
+    to = lambda d: {k: v.cuda() for k, v in d.items()}  # noqa: E731
+    ca, uca, cb, ucb, xa, xb = to(ca), to(uca), to(cb), to(ucb), xa.cuda(), xb.cuda()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    na, nb = torch.randn(xa.shape, generator=g, device="cuda"), torch.randn(xa.shape, generator=g, device="cuda")
+    e1 = Stage2Engine(small)
+    e1.set_condition(ca, uca)
+    ra, _ = e1.step(xa, 5, na, 0.0)
+    e1.set_condition(cb, ucb)
+    rb, _ = e1.step(xb, 5, nb, 0.0)
+    e2 = Stage2Engine(small)
+    cat = lambda a, b: {k: torch.cat((a[k], b[k]), 0) for k in a}  # noqa: E731
+    e2.set_condition(cat(ca, cb), cat(uca, ucb))
+    rab, _ = e2.step(torch.cat((xa, xb), 0), 5, torch.cat((na, nb), 0), 0.0)
+    assert rel_l2(rab[:1] - xa, ra - xa) < 5e-3 and rel_l2(rab[1:] - xb, rb - xb) < 5e-3
+    e3 = Stage2Engine(small, precompute_emb=False)
+    e3.set_condition(ca, uca)
+    rc, _ = e3.step(xa, 5, na, 0.0)
+    assert rel_l2(rc - xa, ra - xa) < 2e-3

@@ -1,7 +1,9 @@
-"""Config 4 on real GPUs: one 256^2 latent (2048^2 image), 128^2 tiles with stride 96 (9 windows) sharded over
-the ranks with NVLink P2P halo exchange (NCCL send/recv).  Checks N-GPU == 1-GPU and reports steps/s.
+"""Config 4 on real GPUs: a pool of 256^2 latents (2048^2 images), 128^2 tiles with stride 96 (9 windows each); the
+(image, window) list is sharded over the ranks with the NVLink halo exchange (NCCL send/recv of the overlap strips).
+Asserts N-GPU == 1-GPU BIT FOR BIT (rank 0 recomputes the whole list alone) and reports tiled steps/s.
 
-  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/tiled_multi_gpu.py [--steps K] [--test-config]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/tiled_multi_gpu.py \
+      [--images P] [--steps K] [--tile-batch B] [--test-config]
 """
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,13 +11,15 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "remote-sensing-
 import torch
 import torch.distributed as dist
 from b200sr import modules, ops
-from b200sr.parallel import TileShardedStepper
+from b200sr.parallel import EngineTileRunner, PooledTileStepper
 from b200sr.sampling import Stage2Engine
-from oracle import configs, inputs, weights
+from oracle import configs, weights
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--images", type=int, default=1)
 ap.add_argument("--latent", type=int, default=256)
+ap.add_argument("--tile-batch", type=int, default=1)
 ap.add_argument("--test-config", action="store_true", help="reduced transformer depth (fast build)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -27,60 +31,57 @@ ucfg, ccfg = (configs.STAGE2_UNET_TEST, configs.STAGE2_CONTROL_TEST) if args.tes
 w = modules.build_stage2(ucfg, ccfg).eval()
 weights.fill_(w.state_dict(), 0)
 w = w.to(dev)
-L = args.latent
+L, P = args.latent, args.images
 g = torch.Generator().manual_seed(4321)                     # identical on every rank
-x = torch.randn(1, 4, L, L, generator=g) * (1 + 14.6146**2) ** 0.5
-lq = torch.randn(1, 4, L, L, generator=g)
-c = {"crossattn": torch.randn(1, 77, 2048, generator=g), "vector": torch.randn(1, 2816, generator=g)}
-uc = {"crossattn": torch.randn(1, 77, 2048, generator=g), "vector": torch.randn(1, 2816, generator=g)}
-noises = [torch.randn(1, 4, L, L, generator=g) for _ in range(args.steps)]
-x, lq = x.to(dev), lq.to(dev)
-c = {k: v.to(dev) for k, v in c.items()}; uc = {k: v.to(dev) for k, v in uc.items()}
-noises = [n.to(dev) for n in noises]
-eng = Stage2Engine(w, device=dev)
-_cnt_scratch = torch.zeros(1, 4, L, L, device=dev)
+xs = {m: torch.randn(1, 4, L, L, generator=g) * (1 + 14.6146**2) ** 0.5 for m in range(P)}
+lqs = {m: torch.randn(1, 4, L, L, generator=g) for m in range(P)}
+caps = {m: tuple({"crossattn": torch.randn(1, 77, 2048, generator=g), "vector": torch.randn(1, 2816, generator=g)}
+                 for _ in range(2)) for m in range(P)}
+noises = {m: [torch.randn(1, 4, L, L, generator=g) for _ in range(args.steps)] for m in range(P)}
 
 
-def accumulate(tile, weight, acc, h0, w0):
-    ops.tile_accumulate(tile, weight, acc, _cnt_scratch, h0, w0)   # count is data independent: kept by the stepper
+def run(solo: bool):
+    st = PooledTileStepper(P, L, L, 128, 96, device=dev, tile_batch=args.tile_batch, blend=ops)
+    if solo:
+        st.world, st.rank, st.mine, st.my_images, st.strips = 1, 0, list(st.units), list(range(P)), {}
+    mine = st.my_images
+    runner = EngineTileRunner(lambda: Stage2Engine(w, device=dev),
+                              {m: tuple({k: v.to(dev) for k, v in d.items()} for d in caps[m]) for m in mine},
+                              {m: lqs[m].to(dev) for m in mine})
+    out = None
+    for rep in range(2):                                    # rep 0 = warm-up (graph capture, weight packing, snapshots)
+        cur = {m: xs[m].to(dev) for m in mine}
+        torch.cuda.synchronize()
+        if world > 1 and not solo:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            cur = st.step(cur, i, {m: noises[m][i].to(dev) for m in mine}, runner)
+        torch.cuda.synchronize()
+        if world > 1 and not solo:
+            dist.barrier()
+        dt = (time.perf_counter() - t0) / args.steps
+        out = cur
+    runner.close()
+    return st, out, dt
 
 
-def run(stepper, sync=True):
-    xx = x.clone()
-    def step_fn(x_tile, i, noise_tile, win):
-        h0, h1, w0, w1 = win
-        lqt = lq[:, :, h0:h1, w0:w1].contiguous()
-        eng.set_condition(dict(c, control=lqt), dict(uc, control=lqt))
-        out, _ = eng.step(x_tile, i, noise_tile, 0.0)
-        return out
-    torch.cuda.synchronize()
-    if world > 1 and sync: dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        xx = stepper.step(xx, i, noises[i], step_fn, accumulate)
-    torch.cuda.synchronize()
-    if world > 1 and sync: dist.barrier()
-    return xx, (time.perf_counter() - t0) / args.steps
-
-st = TileShardedStepper(L, L, 128, 96, device=dev)
-run(st)                                                     # warm-up (graph capture, weight packing)
-out, dt = run(st)
-full = st.gather_full(out)
-res = {"n_gpus": world, "windows": len(st.windows), "windows_per_rank": [len(p) for p in st.parts],
-       "s_per_tiled_step": dt, "tiled_steps_per_s": 1.0 / dt, "halo_bytes_per_step_rank0": st.halo_bytes_per_step}
+st, out, dt = run(False)
+like = torch.zeros(1, 4, L, L, device=dev)
+fulls = [st.gather_image(m, out.get(m), like) for m in range(P)]
+res = {"n_gpus": world, "images": P, "units": len(st.units), "units_per_rank": [len(p) for p in st.parts],
+       "tile_batch": args.tile_batch, "s_per_tiled_step": dt, "tiled_steps_per_s": 1.0 / dt,
+       "halo_bytes_per_step_rank0": st.halo_bytes_per_step, "rank_pairs_exchanging": len(st.strips)}
 if world > 1:
-    # reference: rank 0 recomputes all windows alone and compares
-    solo = TileShardedStepper.__new__(TileShardedStepper)
-    solo.__dict__.update(st.__dict__)
-    solo.world, solo.rank, solo.mine, solo.plan = 1, 0, list(st.windows), {}
     if rank == 0:
-        ref, dt1 = run(solo, sync=False)
-        res["max_abs_diff_vs_1gpu"] = (full - ref).abs().max().item()
-        res["rel_l2_vs_1gpu"] = ((full - ref).norm() / ref.norm()).item()
+        _, ref, dt1 = run(True)
+        res["bitwise_equal_to_1gpu"] = all(torch.equal(fulls[m], ref[m]) for m in range(P))
+        res["max_abs_diff_vs_1gpu"] = max((fulls[m] - ref[m]).abs().max().item() for m in range(P))
         res["s_per_tiled_step_1gpu"] = dt1
         res["speedup"] = dt1 / dt
     dist.barrier()
 if rank == 0:
     print(json.dumps(res))
+    assert res.get("bitwise_equal_to_1gpu", True), "N-GPU result differs from the 1-GPU result"
 if world > 1:
     dist.destroy_process_group()
