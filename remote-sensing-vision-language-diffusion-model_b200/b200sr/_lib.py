@@ -47,6 +47,21 @@ class Copy(C.Structure):
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("bytes", c_i64)]
 
 
+def binding_snippet() -> str:
+    """The struct declarations of this binding as the ctypes source a maintainer would paste (INTEGRATION.md
+    section 1 embeds exactly this text; tests/test_abi_cpu.py diffs the two so the document cannot go stale)."""
+    names = {c_void_p: "C.c_void_p", c_int: "C.c_int32", c_i64: "C.c_int64", c_float: "C.c_float"}
+    out = []
+    for cls, cname in ((Epilogue, "b200sr_epilogue"), (Copy, "b200sr_copy")):
+        out.append(f"class {cls.__name__}(C.Structure):  # {cname} (ABI version {ABI_VERSION})")
+        out.append("    _fields_ = [")
+        for fname, ftype in cls._fields_:
+            out.append(f'        ("{fname}", {names[ftype]}),')
+        out.append("    ]")
+        out.append("")
+    return "\n".join(out).rstrip() + "\n"
+
+
 P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/b200sr.h declares.
 SIGNATURES = {

@@ -932,8 +932,7 @@ class ControlWrapper(nn.Module):
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, control_scale=1, fbcache_mode="none",
                 partial_info=None, **kwargs):
-        if not x.is_cuda:
-            raise RuntimeError("b200sr.ControlWrapper runs on CUDA (sm_100a) only; there is no CPU fallback")
+        ops.require_cuda(x, "b200sr.ControlWrapper")
         control = None
         if fbcache_mode != "input_stage2":
             control = self.control_model(x=c.get("control", None), timesteps=t, xt=x,

@@ -80,6 +80,12 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise _lib.B200SRError(f"{name}: expected a contiguous tensor")
 
 
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    """The product path refuses host tensors up front (there is no CPU fallback)."""
+    if not t.is_cuda:
+        raise _lib.B200SRError(f"{what} runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
 _ws_cache: dict = {}
 _ws_retired: list = []  # outgrown scratch buffers: never freed, captured CUDA graphs may still hold their addresses
 _ws_slot = [0]  # scratch buffers are per (device, slot): work issued concurrently on a second stream uses slot 1

@@ -251,8 +251,7 @@ class UNet(nn.Module, Packed):
         return _linear(self, "t3", self.noise_level_mlp[3], h)
 
     def forward(self, x, time):
-        if not x.is_cuda:
-            raise RuntimeError("b200sr.sr3.UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
+        ops.require_cuda(x, "b200sr.sr3.UNet")
         return self._forward_impl(x, time)
 
     def _forward_impl(self, x, time):

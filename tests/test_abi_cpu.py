@@ -72,6 +72,29 @@ def test_epilogue_struct_layout_matches_a_c_compiler(tmp_path):
         assert getattr(_lib.Epilogue, name).offset == off, name
 
 
+def test_integration_doc_embeds_the_current_binding():
+    """INTEGRATION.md section 1 shows the struct declarations a maintainer pastes: they must be the binding's own
+    (generated) text, field for field — a stale snippet mis-lays the struct silently."""
+    from b200sr import _lib
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert _lib.binding_snippet() in doc, "INTEGRATION.md struct snippet differs from b200sr._lib (regenerate it)"
+    assert f"`b200sr_abi_version()` ({_lib.ABI_VERSION})" in doc
+
+
+def test_copy_struct_layout_matches_a_c_compiler(tmp_path):
+    from b200sr import _lib
+
+    prog = ('#include <stdio.h>\n#include <stddef.h>\n#include "b200sr.h"\nint main(void) {\n'
+            '  printf("%zu %zu %zu %zu\\n", sizeof(b200sr_copy), offsetof(b200sr_copy, src), offsetof(b200sr_copy, dst), '
+            'offsetof(b200sr_copy, bytes));\n  return 0;\n}\n')
+    src, exe = tmp_path / "copy.c", tmp_path / "copy"
+    src.write_text(prog)
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out == [ctypes.sizeof(_lib.Copy), _lib.Copy.src.offset, _lib.Copy.dst.offset, _lib.Copy.bytes.offset]
+
+
 def test_size_queries_work_without_a_device(lib):
     lib.b200sr_group_norm_workspace_bytes.restype = ctypes.c_size_t
     lib.b200sr_attention_d64_workspace_bytes.restype = ctypes.c_size_t
