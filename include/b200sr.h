@@ -79,9 +79,12 @@ int b200sr_gemm_bf16(const void* A, int64_t lda, const void* W, int32_t M, int32
  * implicit GEMM on the same tcgen05 mainloop (each tap = one shifted TMA box, zero fill = pad).
  * Replaces nn.Conv2d 3x3: openaimodel.py:121 (Upsample.conv), :190-197 (Downsample.op),
  * :257 / :294-300 (ResBlock), SR_modules.py:76-80 (ZeroSFT mlp_shared / zero_mul / zero_add),
- * sr3_modules/unet.py:59-92.  Cin % 64 == 0, Cout % 8 == 0.                                   */
+ * sr3_modules/unet.py:59-92; the first-stage convolutions sgm/modules/diffusionmodules/model.py:53-143.
+ * Cin % 64 == 0, Cout % 8 == 0.  pad_lo = 1: pad 1 on every side.  pad_lo = 0 (stride 2 only): pad 0 on top / left and
+ * 1 on bottom / right — the first stage's Downsample, F.pad(x, (0, 1, 0, 1)) + conv(stride 2, padding 0),
+ * model.py:70-88.                                                                                          */
 int b200sr_conv3x3_bf16(const void* x, const void* w, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                        int32_t stride, const b200sr_epilogue* epi, int32_t force_bn, void* stream);
+                        int32_t stride, int32_t pad_lo, const b200sr_epilogue* epi, int32_t force_bn, void* stream);
 
 /* Direct 3x3 convolution (pad 1, stride 1) for tiny channel counts: Cin <= 8 (Cout % 8 == 0),
  * or Cout <= 4 (Cin % 8 == 0).  `addend` (bf16 NHWC, few-in only) is added to the result
@@ -180,6 +183,16 @@ int b200sr_tile_weighted_strip(const float* tile, const float* weight, float* st
                                int32_t y0, int32_t x0, int32_t sh, int32_t sw, void* stream);
 int b200sr_strip_add(const float* strip, float* acc, int32_t BC, int32_t sh, int32_t sw, int32_t H, int32_t W,
                      int32_t h0, int32_t w0, void* stream);
+
+/* First-stage (SDXL VAE) glue at the latent (sgm/models/autoencoder.py:298-318, models/SR_model.py:58-85):
+ *   pointwise_small: 1x1 convolution between <= 8 channels (quant_conv 8->8, post_quant_conv 4->4), bf16 NHWC in,
+ *                    w fp32 [Cout, Cin], out = (w x + bias) * scale as bf16 NHWC or fp32 NCHW [rows / HW, Cout, HW]
+ *   diag_gaussian:   DiagonalGaussianDistribution on moments fp32 NCHW [N, 2C, HW] (mean | logvar, logvar clamped to
+ *                    [-30, 20]): z = (mean + exp(logvar / 2) * noise) * scale, or mean * scale when noise is NULL (mode) */
+int b200sr_pointwise_small(const void* x, const float* w, const float* bias, void* y, int32_t Cin, int32_t Cout,
+                           int64_t rows, int32_t HW, int32_t out_nchw_f32, float scale, void* stream);
+int b200sr_diag_gaussian(const float* moments, const float* noise, float* z, int32_t N, int32_t C, int32_t HW,
+                         float scale, void* stream);
 
 /* Up to 8 small device-to-device copies in one launch (bytes % 4 == 0, 4-byte aligned): the per-step loader of
  * the sampler engine (latent, noise, this step's row of the scalar table sampling.py:598-606 and of the

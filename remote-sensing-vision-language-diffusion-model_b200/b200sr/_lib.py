@@ -68,7 +68,9 @@ SIGNATURES = {
     "b200sr_abi_version": (c_int, []),
     "b200sr_num_sms": (c_int, []),
     "b200sr_gemm_bf16": (c_int, [P, c_i64, P, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
-    "b200sr_conv3x3_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
+    "b200sr_conv3x3_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
+    "b200sr_pointwise_small": (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_int, c_float, P]),
+    "b200sr_diag_gaussian": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "b200sr_conv3x3_small": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200sr_group_norm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200sr_group_norm_nhwc": (

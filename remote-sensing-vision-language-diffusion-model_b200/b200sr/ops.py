@@ -255,9 +255,10 @@ def conv3x3(
     act: int = 0,
     out: Optional[torch.Tensor] = None,
     force_bn: int = 0,
+    pad_lo: int = 1,
 ) -> torch.Tensor:
     """3x3 conv, pad 1.  x: [N, H, W, Cin] bf16; w: packed [Cout, 9*Cin]; rowvec: fp32 [N, Cout]
-    (added per image: ResBlock emb); residual: bf16 [N, OH, OW, Cout]."""
+    (added per image: ResBlock emb); residual: bf16 [N, OH, OW, Cout].  pad_lo = 0 (stride 2): pad (0, 1, 0, 1)."""
     _req(x, bf16, "conv3x3.x")
     _req(w, bf16, "conv3x3.w")
     n, h, wd, cin = x.shape
@@ -271,7 +272,7 @@ def conv3x3(
     e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha, act)
     with _Timed("conv3x3", 2.0 * n * oh * ow * cout * 9 * cin, f"{n}x{h}x{wd} Cin{cin} Cout{cout} s{stride}"):
         rc = _lib.load().b200sr_conv3x3_bf16(
-            x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, C.byref(e), force_bn, _stream()
+            x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, pad_lo, C.byref(e), force_bn, _stream()
         )
     check(rc, f"conv3x3 N={n} H={h} W={wd} Cin={cin} Cout={cout} s={stride}")
     return out
@@ -383,6 +384,31 @@ def softmax_rows(x: torch.Tensor, scale: float = 1.0, valid_cols: Optional[int] 
     return y
 
 
+SCORE_CHUNK_BYTES = 256 << 20   # fp32 score rows held at once by single_head_attention (about two L2s)
+
+
+def single_head_attention(q: torch.Tensor, k: torch.Tensor, v_t: torch.Tensor, scale: float,
+                          out_bias: Optional[torch.Tensor] = None, valid_keys: Optional[int] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v for ONE head of width C = 512 (SR3 SelfAttention, sr3_modules/unet.py:114-143; the
+    first stage's AttnBlock, sgm/modules/diffusionmodules/model.py:158-199).  q, k: [T, C] bf16; v_t: [C, Tk] bf16
+    (V transposed = the B operand of P V); returns [T, C] bf16 (+ out_bias[C]).
+
+    The output accumulator of a 128-row tile at C = 512 fills all 512 TMEM columns, which leaves no room for the score
+    tile, so this shape runs as score GEMM -> row softmax -> P V GEMM over query chunks sized to keep the fp32 scores
+    within SCORE_CHUNK_BYTES (never the T x T matrix: 17 GB at T = 65536)."""
+    t, c = q.shape
+    tk = k.shape[0]
+    rows = (SCORE_CHUNK_BYTES // (4 * tk)) // 256 * 256
+    rows = max(256, min(rows, t))
+    out = torch.empty(t, c, dtype=bf16, device=q.device)
+    for r0 in range(0, t, rows):
+        r1 = min(t, r0 + rows)
+        s = gemm(q[r0:r1], k, out_fp32=True, w_dynamic=True)                    # [rows, Tk] fp32 scores
+        p = softmax_rows(s, scale, valid_cols=valid_keys)
+        gemm(p, v_t, out_bias, w_dynamic=True, out=out[r0:r1])
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # layout / elementwise
 # ------------------------------------------------------------------------------------------------
@@ -459,6 +485,30 @@ def pack_conv3x3_padded(weight: torch.Tensor, cin_pad: int) -> torch.Tensor:
     w = torch.zeros(co, 3, 3, cin_pad, dtype=weight.dtype, device=weight.device)
     w[..., :ci] = weight.detach().permute(0, 2, 3, 1)
     return w.reshape(co, 9 * cin_pad).to(bf16).contiguous()
+
+
+def pointwise_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, out_nchw_f32: bool = False,
+                    scale: float = 1.0) -> torch.Tensor:
+    """1x1 convolution between <= 8 channels: x bf16 [N, H, W, Cin], w fp32 [Cout, Cin] -> (w x + b) * scale as bf16
+    [N, H, W, Cout] or fp32 [N, Cout, H, W]."""
+    _req(x, bf16, "pointwise_small.x")
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    y = (torch.empty(n, cout, h, wd, dtype=torch.float32, device=x.device) if out_nchw_f32
+         else torch.empty(n, h, wd, cout, dtype=bf16, device=x.device))
+    check(_lib.load().b200sr_pointwise_small(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), cin, cout, n * h * wd,
+                                             h * wd, int(out_nchw_f32), float(scale), _stream()), "pointwise_small")
+    return y
+
+
+def diag_gaussian(moments: torch.Tensor, noise: Optional[torch.Tensor], scale: float = 1.0) -> torch.Tensor:
+    """moments fp32 [N, 2C, H, W] -> (mean + exp(clamp(logvar) / 2) * noise) * scale (noise None: the mode)."""
+    _req(moments, torch.float32, "diag_gaussian.moments")
+    n, c2, h, w = moments.shape
+    z = torch.empty(n, c2 // 2, h, w, dtype=torch.float32, device=moments.device)
+    check(_lib.load().b200sr_diag_gaussian(moments.data_ptr(), _ptr(noise), z.data_ptr(), n, c2 // 2, h * w, float(scale),
+                                           _stream()), "diag_gaussian")
+    return z
 
 
 def silu(x: torch.Tensor) -> torch.Tensor:

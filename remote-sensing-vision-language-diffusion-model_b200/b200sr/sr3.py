@@ -163,9 +163,7 @@ class SelfAttention(nn.Module, Packed):
                 tok[:t].copy_(n[i])
             q, k = ops.gemm(tok, wq), ops.gemm(tok, wk)            # [T, C]
             v_t = ops.gemm(wv, tok, w_dynamic=True)                          # [C, T]  (V transposed: B operand of P @ V)
-            s = ops.gemm(q, k, out_fp32=True, w_dynamic=True)                # [T, T] fp32 scores
-            p = ops.softmax_rows(s, 1.0 / math.sqrt(c), valid_cols=t)
-            o_i = ops.gemm(p, v_t, w_dynamic=True)                           # [T, C]
+            o_i = ops.single_head_attention(q, k, v_t, 1.0 / math.sqrt(c), valid_keys=t)   # query chunks, never T x T
             outs.append(o_i if tp == t else o_i[:t].contiguous())
         o = outs[0].unsqueeze(0) if b == 1 else torch.stack(outs, 0)
         y = _linear(self, "out", self.out, o.reshape(b, h * w, c), residual=x.view(b, h * w, c))

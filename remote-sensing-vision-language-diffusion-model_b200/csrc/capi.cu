@@ -78,8 +78,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ---- forward declarations of the kernel launchers -------------------------------------------
 int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, const EpilogueArgs& e, int force_bn,
               cudaStream_t stream);
-int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride,
+int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride, int pad_lo,
                  const EpilogueArgs& e, int force_bn, cudaStream_t stream);
+int pointwise_small(const void* x, const float* w, const float* bias, void* y, int Cin, int Cout, long long rows, int HW,
+                    int out_nchw_f32, float scale, cudaStream_t stream);
+int diag_gaussian(const float* moments, const float* noise, float* z, int N, int C, int HW, float scale,
+                  cudaStream_t stream);
 size_t group_norm_workspace_bytes(int N, int HW, int C, int groups);
 int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int N, int HW, int C, int groups,
                     float eps, int silu, const void* sft_gamma, const void* sft_beta, const void* raw,
@@ -163,9 +167,19 @@ int b200sr_gemm_bf16(const void* A, int64_t lda, const void* W, int32_t M, int32
   return gemm_bf16(A, lda, W, M, N, K, to_args(epi), force_bn, S(stream));
 }
 int b200sr_conv3x3_bf16(const void* x, const void* w, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                        int32_t stride, const b200sr_epilogue* epi, int32_t force_bn, void* stream) {
+                        int32_t stride, int32_t pad_lo, const b200sr_epilogue* epi, int32_t force_bn, void* stream) {
   if (x == nullptr || w == nullptr || epi == nullptr) return B200SR_EINVAL;
-  return conv3x3_bf16(x, w, N, H, W, Cin, Cout, stride, to_args(epi), force_bn, S(stream));
+  return conv3x3_bf16(x, w, N, H, W, Cin, Cout, stride, pad_lo, to_args(epi), force_bn, S(stream));
+}
+int b200sr_pointwise_small(const void* x, const float* w, const float* bias, void* y, int32_t Cin, int32_t Cout,
+                           int64_t rows, int32_t HW, int32_t out_nchw_f32, float scale, void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr) return B200SR_EINVAL;
+  return pointwise_small(x, w, bias, y, Cin, Cout, rows, HW, out_nchw_f32, scale, S(stream));
+}
+int b200sr_diag_gaussian(const float* moments, const float* noise, float* z, int32_t N, int32_t C, int32_t HW,
+                         float scale, void* stream) {
+  if (moments == nullptr || z == nullptr) return B200SR_EINVAL;
+  return diag_gaussian(moments, noise, z, N, C, HW, scale, S(stream));
 }
 int b200sr_conv3x3_small(const void* x, const void* w, const float* bias, const void* addend, void* y, int32_t N,
                          int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t out_nchw_f32, void* stream) {

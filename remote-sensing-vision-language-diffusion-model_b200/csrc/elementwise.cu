@@ -751,4 +751,74 @@ int strip_add(const float* strip, float* acc, int BC, int sh, int sw, int H, int
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
+// ------------------------------------------------------------------------------------------
+// First-stage (SDXL VAE) glue around the latent: 1x1 convolutions between <= 8 channels
+//   quant_conv 8 -> 8 and post_quant_conv 4 -> 4            sgm/models/autoencoder.py:298-299, :305-318
+// one thread per pixel, weights in shared memory, fp32 math; bf16 NHWC in, bf16 NHWC or fp32 NCHW (x scale) out;
+// and DiagonalGaussianDistribution.sample / .mode        sgm/modules/distributions/distributions.py (mean | logvar
+// halves of the moments, logvar clamped to [-30, 20], z = mean + exp(0.5 logvar) * noise), times scale_factor
+// (models/SR_model.py:58-78).
+// ------------------------------------------------------------------------------------------
+__global__ void pointwise_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                       const float* __restrict__ bias, void* __restrict__ y, int Cin, int Cout,
+                                       long long rows, int HW, int out_nchw_f32, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_w[64], s_b[8];
+  if (threadIdx.x < Cin * Cout) s_w[threadIdx.x] = w[threadIdx.x];
+  if (threadIdx.x < Cout) s_b[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+       r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float xv[8], acc[8];
+    for (int c = 0; c < Cin; ++c) xv[c] = __bfloat162float(x[r * Cin + c]);
+    for (int o = 0; o < Cout; ++o) {
+      float a = s_b[o];
+      for (int c = 0; c < Cin; ++c) a = fmaf(xv[c], s_w[o * Cin + c], a);
+      acc[o] = a * scale;
+    }
+    if (out_nchw_f32) {
+      const long long n = r / HW, pix = r - n * HW;
+      for (int o = 0; o < Cout; ++o) reinterpret_cast<float*>(y)[(n * Cout + o) * HW + pix] = acc[o];
+    } else {
+      for (int o = 0; o < Cout; ++o) reinterpret_cast<__nv_bfloat16*>(y)[r * Cout + o] = __float2bfloat16(acc[o]);
+    }
+  }
+}
+int pointwise_small(const void* x, const float* w, const float* bias, void* y, int Cin, int Cout, long long rows, int HW,
+                    int out_nchw_f32, float scale, cudaStream_t stream) {
+  if (Cin <= 0 || Cin > 8 || Cout <= 0 || Cout > 8 || rows <= 0 || HW <= 0 || (rows % HW) != 0) return B200SR_EINVAL;
+  int grid = static_cast<int>((rows + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  launch_k(pointwise_small_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x), w, bias, y, Cin,
+           Cout, rows, HW, out_nchw_f32, scale);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+__global__ void diag_gaussian_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                     float* __restrict__ z, int C, int HW, long long total, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / (static_cast<long long>(C) * HW), rem = i - n * C * HW;
+    const float mean = moments[n * 2 * C * HW + rem];
+    float v = mean;
+    if (noise != nullptr) {
+      const float logvar = fminf(fmaxf(moments[n * 2 * C * HW + static_cast<long long>(C) * HW + rem], -30.f), 20.f);
+      v = mean + expf(0.5f * logvar) * noise[i];
+    }
+    z[i] = v * scale;
+  }
+}
+int diag_gaussian(const float* moments, const float* noise, float* z, int N, int C, int HW, float scale,
+                  cudaStream_t stream) {
+  if (N <= 0 || C <= 0 || HW <= 0) return B200SR_EINVAL;
+  const long long total = static_cast<long long>(N) * C * HW;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  launch_k(diag_gaussian_kernel, dim3(grid), dim3(256), 0, stream, 1, moments, noise, z, C, HW, total, scale);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
 }  // namespace b200sr

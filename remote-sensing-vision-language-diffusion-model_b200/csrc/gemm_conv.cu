@@ -74,6 +74,7 @@ struct GemmParams {
   int k_iters;
   int kc_per_tap;
   int Cin;
+  int pad_lo;  // mode 2: 1 = pad 1 on every side; 0 = pad (0, 1, 0, 1) (bottom / right only: the VAE Downsample)
   int OH, OW, NB;
   int bw_log2, bh_log2, bn_log2;
   int tiles_w, tiles_h, tiles_n;
@@ -425,8 +426,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               kw = tap - kh * 3;
               kb = tap * p.Cin + c0;
             }
-            // input row 2*oh + kh - 1  ->  (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
-            const int hp = (kh == 1) ? 0 : 1, wp = (kw == 1) ? 0 : 1;
+            // pad_lo = 1: input row 2*oh + kh - 1 -> (h2, parity): kh=0 -> (oh-1, 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1)
+            // pad_lo = 0: input row 2*oh + kh     ->               kh=0 -> (oh, 0),   kh=1 -> (oh, 1), kh=2 -> (oh+1, 0)
+            const int hp = p.pad_lo ? ((kh == 1) ? 0 : 1) : (kh & 1), wp = p.pad_lo ? ((kw == 1) ? 0 : 1) : (kw & 1);
+            const int dh = p.pad_lo ? -(kh == 0) : (kh == 2), dw = p.pad_lo ? -(kw == 0) : (kw == 2);
             if (kCluster == 1) {
               if (!w_only) {
                 if (p.mode == 0)
@@ -434,7 +437,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 else if (p.mode == 1)
                   tma_load_4d(sa, &tmA, &full_bar[st], c0, w0 + kw - 1, h0 + kh - 1, i0);
                 else
-                  tma_load_5d(sa, &tmA, &full_bar[st], wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+                  tma_load_5d(sa, &tmA, &full_bar[st], wp * p.Cin + c0, w0 + dw, hp, h0 + dh, i0);
               }
               if (!a_only) tma_load_2d(sb, &tmB, &full_bar[st], kb, n0);
             } else {
@@ -444,7 +447,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 else if (p.mode == 1)
                   tma2_load_4d(sa, &tmA, bar, c0, w0 + kw - 1, h0 + kh - 1, i0);
                 else
-                  tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 - (kw == 0), hp, h0 - (kh == 0), i0);
+                  tma2_load_5d(sa, &tmA, bar, wp * p.Cin + c0, w0 + dw, hp, h0 + dh, i0);
               }
               if (!a_only) tma2_load_2d(sb, &tmB, bar, kb, n0);
             }
@@ -938,10 +941,11 @@ int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, 
 }
 
 // x: NHWC bf16 [NB, H, W, Cin]; w: [Cout, 3, 3, Cin] bf16 (K = tap*Cin + c); stride 1 or 2, pad 1.
-int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride,
+int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride, int pad_lo,
                  const EpilogueArgs& e, int force_bn, cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin % BLOCK_K) != 0 || Cout <= 0) return B200SR_EINVAL;
   if (stride != 1 && stride != 2) return B200SR_EINVAL;
+  if (pad_lo != 1 && !(pad_lo == 0 && stride == 2)) return B200SR_EINVAL;
   if (stride == 2 && ((H | W) & 1)) return B200SR_EINVAL;
   if (e.geglu) return B200SR_EINVAL;
   const int OH = H / stride, OW = W / stride;
@@ -968,6 +972,7 @@ int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, in
   p.OH = OH;
   p.OW = OW;
   p.Cin = Cin;
+  p.pad_lo = pad_lo;
   p.M = NB * OH * OW;
   p.N = Cout;
   p.K = 9 * Cin;

@@ -56,11 +56,16 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu
     return y
 
 
-def conv3x3(x, w, bias=None, *, stride=1, rowvec=None, residual=None, alpha=1.0, act=0, out=None, force_bn=0):
+def conv3x3(x, w, bias=None, *, stride=1, rowvec=None, residual=None, alpha=1.0, act=0, out=None, force_bn=0, pad_lo=1):
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     w4 = w.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w4, bias, stride=stride, padding=1) * 1.0
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad_lo == 0:
+        assert stride == 2
+        y = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w4, bias, stride=2, padding=0) * 1.0
+    else:
+        y = F.conv2d(xin, w4, bias, stride=stride, padding=1) * 1.0
     if alpha != 1.0:
         y = y * alpha
     if rowvec is not None:
@@ -119,6 +124,15 @@ def attention(q, k, v, heads, *, q_col=0, k_col=0, v_col=0, scale=None):
     return (att @ vf).transpose(1, 2).reshape(b, nq, c).to(bf16)
 
 
+def single_head_attention(q, k, v_t, scale, out_bias=None, valid_keys=None):
+    s = q.float() @ k.float().t()
+    p = softmax_rows(s, scale, valid_cols=valid_keys).float()
+    o = p @ v_t.float().t()
+    if out_bias is not None:
+        o = o + out_bias
+    return o.to(bf16)
+
+
 def softmax_rows(x, scale=1.0, valid_cols=None):
     v = x.shape[-1] if valid_cols is None else valid_cols
     y = torch.zeros_like(x, dtype=torch.float32)
@@ -160,6 +174,18 @@ def pad_channels(x, cpad):
 
 def silu(x):
     return F.silu(x.float()).to(bf16)
+
+
+def pointwise_small(x, w, bias, *, out_nchw_f32=False, scale=1.0):
+    y = F.linear(x.float(), w.float(), bias) * scale
+    return y.permute(0, 3, 1, 2).contiguous() if out_nchw_f32 else y.to(bf16)
+
+
+def diag_gaussian(moments, noise, scale=1.0):
+    mean, logvar = moments.chunk(2, dim=1)
+    if noise is None:
+        return mean * scale
+    return (mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) * scale
 
 
 def sinusoid_embedding(t, dim, max_period=10000.0, sin_first=False):
