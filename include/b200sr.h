@@ -194,6 +194,17 @@ int b200sr_pointwise_small(const void* x, const float* w, const float* bias, voi
 int b200sr_diag_gaussian(const float* moments, const float* noise, float* z, int32_t N, int32_t C, int32_t HW,
                          float scale, void* stream);
 
+/* Output side (utils/colorfix.py:73-119, models/util.py:159-166), fp32 NCHW images:
+ *   wavelet_level: low = depthwise 3x3 [1 2 1; 2 4 2; 1 2 1] / 16 blur of img with dilation `radius` and replicate
+ *                  padding; if high != NULL: high = (first ? 0 : high) + (img - low)   (one level of wavelet_decomposition)
+ *   add_f32:       out = a + b                                   (content_high_freq + style_low_freq)
+ *   image_to_u8:   bicubic resize (align_corners False, A = -0.75) of one [C, H, W] image in [-1, 1] to [OH, OW],
+ *                  * 127.5 + 127.5, clip, truncate -> uint8 [OH, OW, C]                              (Tensor2PIL) */
+int b200sr_wavelet_level(const float* img, float* low, float* high, int32_t first, int32_t BC, int32_t H, int32_t W,
+                         int32_t radius, void* stream);
+int b200sr_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+int b200sr_image_to_u8(const float* x, void* out, int32_t C, int32_t H, int32_t W, int32_t OH, int32_t OW, void* stream);
+
 /* Up to 8 small device-to-device copies in one launch (bytes % 4 == 0, 4-byte aligned): the per-step loader of
  * the sampler engine (latent, noise, this step's row of the scalar table sampling.py:598-606 and of the
  * precomputed timestep-embedding projections openaimodel.py:281-287) into the buffers a CUDA graph reads. */

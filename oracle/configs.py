@@ -29,3 +29,9 @@ STAGE2_UNET_TEST = reduced(STAGE2_UNET)
 SR3_UNET = dict(in_channel=6, out_channel=3, norm_groups=32, inner_channel=64, channel_mults=[1, 2, 4, 8, 8],
                 attn_res=[28], res_blocks=1, dropout=0.2, image_size=224)
 SR3_SCHEDULE = dict(n_timestep=50, linear_start=1e-6, linear_end=1e-2)  # BASELINE config 1 (reference default: 500)
+
+# first stage (SDXL VAE): model_configs/juggernautXL.yaml:107-125.  attn_type "vanilla-xformers" and "vanilla" compute the
+# same single-head attention (model.py:158-263); the oracle / golden side uses "vanilla" (no xformers in this image).
+VAE_DDCONFIG = dict(attn_type="vanilla", double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                    ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+VAE_EMBED_DIM = 4

@@ -151,6 +151,58 @@ def sr3(size=32, seed=0):
     print("[sr3] wrote golden")
 
 
+def vae(size=64, seed=0):
+    """First stage: real AutoencoderKLInferenceWrapper vs oracle/vae.py; golden = the reference's outputs."""
+    from oracle import vae as ovae
+
+    ref = reference_import.vae_modules(configs.VAE_DDCONFIG, configs.VAE_EMBED_DIM)
+    weights.fill_(ref.state_dict(), seed)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    img = torch.rand(1, 3, size, size, generator=g) * 2 - 1
+    noise = torch.randn(1, 4, size // 8, size // 8, generator=g)
+    with torch.no_grad():
+        m_ref = ref.quant_conv(ref.denoise_encoder(img))                      # SR_model.py:66-71
+        m_plain = ref.quant_conv(ref.encoder(img))
+        z = ovae.SCALE_FACTOR * m_ref.chunk(2, dim=1)[0]                      # posterior.mode() * scale_factor
+        x_ref = ref.decode(1.0 / ovae.SCALE_FACTOR * z)                       # SR_model.py:81-85
+        m_or = ovae.moments(sd, img, "denoise_encoder.")
+        x_or = ovae.decode_first_stage(sd, ovae.encode_with_denoise(sd, img))
+    print(f"[vae] moments |ref|max {m_ref.abs().max():.4f} oracle-vs-ref {maxdiff(m_ref, m_or):.3e}; "
+          f"decode |ref|max {x_ref.abs().max():.4f} oracle-vs-ref {maxdiff(x_ref, x_or):.3e}")
+    assert maxdiff(m_ref, m_or) < 1e-4 * max(1.0, m_ref.abs().max().item())
+    assert maxdiff(x_ref, x_or) < 1e-4 * max(1.0, x_ref.abs().max().item())
+    assert maxdiff(ovae.posterior(m_plain, noise), m_plain.chunk(2, 1)[0] + torch.exp(0.5 * m_plain.chunk(2, 1)[1].clamp(-30, 20)) * noise) == 0
+    torch.save({"size": size, "img": img, "moments": m_ref, "z": z, "decoded": x_ref,
+                "weight_checksum": checksum(sd["decoder.mid.block_1.conv1.weight"])},
+               os.path.join(GOLDEN, f"vae_{size}.pt"))
+    import json
+
+    with open(os.path.join(GOLDEN, "vae_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in sd.items()}, f, indent=0, sort_keys=True)
+    print("[vae] wrote golden")
+
+
+def colorfix(size=48):
+    """Output side: the reference's utils/colorfix.py functions vs oracle/colorfix.py; golden = the reference's outputs."""
+    reference_import.install_stubs()
+    from oracle import colorfix as ocf
+    from utils import colorfix as rcf
+
+    g = torch.Generator().manual_seed(17)
+    content = torch.rand(1, 3, size, size + 16, generator=g) * 2.4 - 1.2
+    style = torch.rand(1, 3, size, size + 16, generator=g) * 2 - 1
+    ref = rcf.wavelet_reconstruction(content, style)
+    assert maxdiff(ref, ocf.wavelet_reconstruction(content, style)) == 0.0
+    hi, lo = rcf.wavelet_decomposition(content)
+    u8_same = ocf.tensor_to_uint8(ref[0], size, size + 16)
+    u8_up = ocf.tensor_to_uint8(ref[0], 70, 100)
+    u8_down = ocf.tensor_to_uint8(ref[0], 31, 40)
+    torch.save({"content": content, "style": style, "reconstruction": ref, "high": hi, "low": lo,
+                "u8_same": u8_same, "u8_up": u8_up, "u8_down": u8_down}, os.path.join(GOLDEN, f"colorfix_{size}.pt"))
+    print("[colorfix] wrote golden")
+
+
 def tables():
     reference_import.install_stubs()
     from sgm.modules.diffusionmodules.sampling import _sliding_windows
@@ -199,6 +251,14 @@ if __name__ == "__main__":
     keys()
     if "--keys-only" in sys.argv:
         sys.exit(0)
+    if "--vae-only" in sys.argv:
+        vae()
+        sys.exit(0)
+    if "--colorfix-only" in sys.argv:
+        colorfix()
+        sys.exit(0)
     tables()
     sr3()
+    vae()
+    colorfix()
     stage2()

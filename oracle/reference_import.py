@@ -96,3 +96,20 @@ def sr3_modules(unet_cfg: dict, schedule: dict):
     diff = GaussianDiffusion(net, image_size=unet_cfg["image_size"], channels=3, loss_type="l1", conditional=True)
     diff.set_new_noise_schedule(dict(schedule, schedule="linear"), device="cpu")
     return diff.eval()
+
+
+def vae_modules(ddconfig: dict, embed_dim: int):
+    """The reference AutoencoderKLInferenceWrapper (sgm/models/autoencoder.py:282-321) with the SR_backbone's
+    denoise_encoder copy (models/SR_model.py:22), eval mode, fp32."""
+    install_stubs()
+    import contextlib
+    import copy
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        from sgm.models.autoencoder import AutoencoderKLInferenceWrapper
+
+        vae = AutoencoderKLInferenceWrapper(embed_dim=embed_dim, ddconfig=dict(ddconfig),
+                                            lossconfig={"target": "torch.nn.Identity"}, monitor="val/rec_loss")
+    vae.denoise_encoder = copy.deepcopy(vae.encoder)
+    return vae.eval()

@@ -99,6 +99,9 @@ SIGNATURES = {
     "b200sr_tile_normalize": (c_int, [P, P, P, c_i64, P]),
     "b200sr_rel_l1_similarity": (c_int, [P, P, c_i64, P, P, P, P]),
     "b200sr_sr3_update": (c_int, [P, P, P, P, P, c_i64, P]),
+    "b200sr_wavelet_level": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200sr_add_f32": (c_int, [P, P, P, c_i64, P]),
+    "b200sr_image_to_u8": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "b200sr_copy_batch": (c_int, [C.POINTER(Copy), c_int, P]),
     "b200sr_tile_weighted_strip": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200sr_strip_add": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

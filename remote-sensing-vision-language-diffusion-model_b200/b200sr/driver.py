@@ -12,7 +12,7 @@ What it runs per image (the denoiser hot path and its closest callers):
 
 The bracketed stages are the rows SURVEY.md section 8(f) ranks after the step path (VAE f2, colour fix f3).  They are
 pluggable: ``first_stage`` is any object with ``encode(img) -> latent`` / ``decode(latent) -> img``
-(``b200sr.vae.AutoencoderKL`` when built); without one the driver stops at the latent and uses
+(``b200sr.vae.FirstStage`` over ``b200sr.vae.AutoencoderKL``); without one the driver stops at the latent and uses
 ``LatentStandIn`` — a fixed linear 8x8 pooling of the stage-1 image into 4 channels — to derive the
 LQ control latent, which keeps shapes, data flow and work per image identical for throughput
 purposes and is labelled as such in every result.  Captions are the fixed synthetic text embeddings
@@ -88,7 +88,10 @@ class RestorationPipeline:
             stage1 = cond
         t1 = self._tic()
         # ---- first stage encode -> LQ control latent (SR_model.py:259-263) -----------------------------------------
-        lq = self.first_stage.encode(stage1)
+        lq = self.first_stage.encode(stage1)                 # _z = encode_first_stage_with_denoise(x, use_sample=False)
+        x_stage1 = self.first_stage.decode(lq)               # x_stage1 = decode_first_stage(_z): the colour-fix reference
+        # (z_stage1 = encode_first_stage(x_stage1), SR_model.py:256, only feeds the restore_cfg > 0 branch of the
+        #  sampler, which the shipped drivers switch off with restoration_scale = -1; it is not computed here.)
         t2 = self._tic()
         # ---- stage 2: num_steps RestoreEDMSampler steps with the first-block cache (SR_model.py:265-291) -------
         cc = {"crossattn": c["crossattn"].to(dev), "vector": c["vector"].to(dev), "control": lq}
@@ -101,12 +104,17 @@ class RestorationPipeline:
         t3 = self._tic()
         # ---- decode, colour fix (SR_model.py:293-298) -------------------------------------------------------------
         img = self.first_stage.decode(z)
-        if img is not None and self.color_fix is not None:
-            img = self.color_fix(img, stage1)
+        u8 = None
+        if img is not None:
+            if self.color_fix is not None:
+                img = self.color_fix(img, x_stage1)                               # wavelet_reconstruction(samples, x_stage1)
+            from .colorfix import tensor_to_uint8
+
+            u8 = tensor_to_uint8(img[0], img.shape[-2], img.shape[-1])            # Tensor2PIL(sample, h0, w0)
         t4 = self._tic()
         for k, v in (("stage1_s", t1 - t0), ("encode_s", t2 - t1), ("stage2_s", t3 - t2), ("decode_s", t4 - t3)):
             self.timings[k] = self.timings.get(k, 0.0) + v
-        return {"stage1": stage1, "latent": z, "image": img, "trace": trace}
+        return {"stage1": stage1, "latent": z, "image": img, "uint8": u8, "trace": trace}
 
 
 def run_sharded(pipeline: RestorationPipeline, images: Sequence[torch.Tensor], captions: Sequence, rank: int = 0,

@@ -634,3 +634,34 @@ def sr3_update(x: torch.Tensor, eps: torch.Tensor, noise: Optional[torch.Tensor]
     check(_lib.load().b200sr_sr3_update(x.data_ptr(), eps.data_ptr(), _ptr(noise), scalars.data_ptr(), out.data_ptr(),
                                         x.numel(), _stream()), "sr3_update")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# output side: wavelet colour fix, Tensor2PIL
+# ------------------------------------------------------------------------------------------------
+def wavelet_level(img: torch.Tensor, radius: int, high: Optional[torch.Tensor] = None, first: bool = False) -> torch.Tensor:
+    """One level of wavelet_decomposition (utils/colorfix.py:73-106): returns low = blur(img, radius); `high`
+    (optional, in place) accumulates img - low."""
+    _req(img, torch.float32, "wavelet_level.img")
+    b, c, h, w = img.shape
+    low = torch.empty_like(img)
+    check(_lib.load().b200sr_wavelet_level(img.data_ptr(), low.data_ptr(), _ptr(high), int(first), b * c, h, w, int(radius),
+                                           _stream()), "wavelet_level")
+    return low
+
+
+def add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _req(a, torch.float32, "add_f32.a")
+    _req(b, torch.float32, "add_f32.b")
+    out = torch.empty_like(a)
+    check(_lib.load().b200sr_add_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "add_f32")
+    return out
+
+
+def image_to_u8(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """fp32 [C, H, W] in [-1, 1] -> uint8 [oh, ow, C] (bicubic resize, *127.5 + 127.5, clip, truncate)."""
+    _req(x, torch.float32, "image_to_u8.x")
+    c, h, w = x.shape
+    out = torch.empty(oh, ow, c, dtype=torch.uint8, device=x.device)
+    check(_lib.load().b200sr_image_to_u8(x.data_ptr(), out.data_ptr(), c, h, w, oh, ow, _stream()), "image_to_u8")
+    return out

@@ -140,8 +140,8 @@ class Stage2Engine:
         self._streams = None
         self.sched = StepSchedule(num_steps, s_churn, 0.0, float("inf"), s_noise, cfg_scale, cfg_scale_min)
         self.control_scale = control_scale
-        self.use_graphs = use_graphs
         self.device = torch.device(device)
+        self.use_graphs = use_graphs and self.device.type == "cuda"
         self._scalars_dev = self.sched.scalars.to(self.device).contiguous()   # [steps, 6]
         self._idx_dev = self.sched.idx.to(self.device)
         self.cond = None

@@ -11,12 +11,12 @@ read -r -a EXTRA <<< "${B200SR_EXTRA_FLAGS:-}"
 FLAGS+=("${EXTRA[@]}")
 mkdir -p "${HERE}/build"
 pids=()
-for f in gemm_conv attention norm elementwise capi; do
+for f in gemm_conv attention norm elementwise image capi; do
   "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/build/${f}.o" 2> "${HERE}/build/${f}.log" &
   pids+=($!)
 done
 rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 if [ $rc -ne 0 ]; then cat "${HERE}"/build/*.log >&2; exit 1; fi
-"${NVCC}" -shared -o "${OUT}" "${HERE}"/build/{gemm_conv,attention,norm,elementwise,capi}.o -lcudart
+"${NVCC}" -shared -o "${OUT}" "${HERE}"/build/{gemm_conv,attention,norm,elementwise,image,capi}.o -lcudart
 echo "built ${OUT}"

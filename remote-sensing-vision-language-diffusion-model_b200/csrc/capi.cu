@@ -120,6 +120,10 @@ int rel_l1_similarity(const void* prev, const void* cur, long long n, const floa
                       float* result, cudaStream_t stream);
 int sr3_update(const float* x, const float* eps, const float* noise, const float* scalars, float* out, long long n,
                cudaStream_t stream);
+int wavelet_level(const float* img, float* low, float* high, int first, int BC, int H, int W, int radius,
+                  cudaStream_t stream);
+int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+int image_to_u8(const float* x, void* out, int C, int H, int W, int OH, int OW, cudaStream_t stream);
 int copy_batch(const void* const* src, void* const* dst, const long long* bytes, int n, cudaStream_t stream);
 int tile_weighted_strip(const float* tile, const float* weight, float* strip, int BC, int th, int tw, int y0, int x0,
                         int sh, int sw, cudaStream_t stream);
@@ -308,6 +312,20 @@ int b200sr_strip_add(const float* strip, float* acc, int32_t BC, int32_t sh, int
                      int32_t h0, int32_t w0, void* stream) {
   if (strip == nullptr || acc == nullptr) return B200SR_EINVAL;
   return strip_add(strip, acc, BC, sh, sw, H, W, h0, w0, S(stream));
+}
+
+int b200sr_wavelet_level(const float* img, float* low, float* high, int32_t first, int32_t BC, int32_t H, int32_t W,
+                         int32_t radius, void* stream) {
+  if (img == nullptr || low == nullptr) return B200SR_EINVAL;
+  return wavelet_level(img, low, high, first, BC, H, W, radius, S(stream));
+}
+int b200sr_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (a == nullptr || b == nullptr || out == nullptr) return B200SR_EINVAL;
+  return add_f32(a, b, out, n, S(stream));
+}
+int b200sr_image_to_u8(const float* x, void* out, int32_t C, int32_t H, int32_t W, int32_t OH, int32_t OW, void* stream) {
+  if (x == nullptr || out == nullptr) return B200SR_EINVAL;
+  return image_to_u8(x, out, C, H, W, OH, OW, S(stream));
 }
 
 }  // extern "C"

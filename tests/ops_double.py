@@ -261,6 +261,26 @@ def sr3_update(x, eps, noise, scalars):
     return out if noise is None else out + noise * math.exp(0.5 * lv)
 
 
+def wavelet_level(img, radius, high=None, first=False):
+    k = torch.tensor([[0.0625, 0.125, 0.0625], [0.125, 0.25, 0.125], [0.0625, 0.125, 0.0625]])[None, None]
+    c = img.shape[1]
+    low = F.conv2d(F.pad(img, (radius,) * 4, mode="replicate"), k.repeat(c, 1, 1, 1), groups=c, dilation=radius)
+    if high is not None:
+        if first:
+            high.zero_()
+        high += img - low
+    return low
+
+
+def add_f32(a, b):
+    return a + b
+
+
+def image_to_u8(x, oh, ow):
+    y = F.interpolate(x[None], size=(oh, ow), mode="bicubic")[0]
+    return (y.permute(1, 2, 0) * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("F", "torch", "math")]
 
 
