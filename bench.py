@@ -19,6 +19,7 @@ scaling).  Beside it, in the same line:
   tiled_x8            BASELINE config 4: a pool of 256^2 latents (2048^2 images), 9 windows each, the (image, window)
                       list sharded over the N ranks with the NVLink halo exchange; tiled steps/s, bytes exchanged,
                       speed-up over the same list on rank 0 alone; single-image scaling beside it
+  batched             the same step with 2 / 4 latents per network call (per-latent step time)
   images_per_s        BASELINE config 5 sample: infer_dir-style images sharded i mod N, SR3 x8 + 50 cached steps
 """
 from __future__ import annotations
@@ -400,6 +401,34 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    # ---- several latents per network call (batching > 1 image per step) ----------------------------
+    batched = None
+    if not args.no_batched:
+        batched = {}
+        for nb in (2, 4):
+            xs, cs, ucs = zip(*(inputs.stage2_inputs(latent=LATENT, seed=1234 + 17 * j + rank) for j in range(nb)))
+            cat = lambda ds: {k: torch.cat([d[k] for d in ds], 0).to(dev) for k in ds[0]}  # noqa: E731
+            engb = Stage2Engine(wrapper, use_graphs=not args.no_graphs, device=dev)
+            engb.set_condition(cat(cs), cat(ucs))
+            xb = torch.cat(xs, 0).to(dev)
+            nzb = torch.randn(xb.shape, device=dev)
+            for _ in range(3):
+                engb.step(xb, step_i, nzb, 0.0, copy_out=False)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(max(4, args.steps // 2)):
+                engb.step(xb, step_i, nzb, 0.0, copy_out=False)
+            b1.record()
+            barrier()
+            msb = b0.elapsed_time(b1) / max(4, args.steps // 2)
+            batched[f"latents_{nb}"] = {"ms_per_step": msb, "ms_per_latent_step": msb / nb,
+                                        "latent_steps_per_s_per_gpu": 1000.0 * nb / msb,
+                                        "tflops": nb * STEP_TFLOP / (msb * 1e-3)}
+            engb.close()
+            del engb
+            torch.cuda.empty_cache()
+
     # ---- multi-GPU blocks (every rank takes part) ----------------------------------------------------
     tiled = images = None
     if not args.no_tiled:
@@ -497,6 +526,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         line["cpu_baseline"] = cpu
     if gpu_eager is not None:
         line["gpu_eager_baseline"] = gpu_eager
+    if batched is not None:
+        line["batched"] = dict(batched, what="the same step with 2 / 4 independent latents per network call (CFG batch 4 / 8): "
+                                             "M = 4096 / 8192-row GEMMs, weights streamed once per call; rank 0's timing")
     if tiled is not None:
         line["tiled_x8"] = tiled
     if images is not None:
@@ -514,6 +546,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-tiled", action="store_true")
+    ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-images", action="store_true")
     ap.add_argument("--tiled-pool", type=int, default=10, help="images in the pooled tiled x8 work list (9 windows each)")
     ap.add_argument("--tiled-steps", type=int, default=2, help="timed tiled sampler steps")

@@ -384,7 +384,7 @@ def softmax_rows(x: torch.Tensor, scale: float = 1.0, valid_cols: Optional[int] 
     return y
 
 
-SCORE_CHUNK_BYTES = 256 << 20   # fp32 score rows held at once by single_head_attention (about two L2s)
+SCORE_CHUNK_BYTES = 1 << 30   # fp32 score rows held at once by single_head_attention (T = 16384: the whole 1 GB matrix)
 
 
 def single_head_attention(q: torch.Tensor, k: torch.Tensor, v_t: torch.Tensor, scale: float,

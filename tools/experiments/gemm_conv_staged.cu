@@ -48,7 +48,8 @@ static constexpr int MAX_STAGES = 8;
 // One pipeline stage = KSUB 64-wide K chunks (modes 0-2) or HALO_TAPS weight tiles (mode 3): the MMA issue thread
 // pays ~150-230 cycles per barrier wait + commit (tools/micro/issue_overhead.cu), which at N <= 192 exceeds the
 // MMAs' own time when it is paid per chunk.
-static constexpr int KSUB = 2;
+static constexpr int KSUB = 2;   // default K chunks per stage (GemmParams::ksub)
+static constexpr int EPI_STAGE_BYTES = 4 * 5120;  // per-warp transposes of the epilogue
 static constexpr int HALO_TAPS = 3;
 // mode 3 ("halo" 3x3 convolution, stride 1): per 64-channel chunk ONE (16+2) x (8+2)-pixel halo tile of the input
 // is staged and the nine taps read it as shifted windows (UMMA descriptor start + (kh * 10 + kw) * 128 B, 8-row
@@ -80,11 +81,11 @@ struct GemmParams {
   int tiles_w, tiles_h, tiles_n;
   int stages;
   int a_stages;  // mode 3: halo-tile ring depth (stages = weight ring depth)
+  int ksub;      // modes 0-2: 64-wide K chunks per pipeline stage (1 or 2)
+  int tmem_cols; // TMEM columns to allocate: 512 (two accumulator stages) or, when every CTA owns a single tile, the
+                 // power of two >= BN so that the CTAs of the NEXT kernel can become resident beside this one
 #ifdef B200SR_GEMM_TRACE
-  long long* trace;  // [grid][16]: 0 mainloop cycles, 1 cycles blocked on the full barrier, 2 chunks, 3 chunks found not ready,
-                     // clock64 stamps: 4 entry, 5 set-up done, 6 producer past griddepcontrol.wait, 7 first stage landed,
-                     // 8 last MMA committed, 9 accumulator visible to the epilogue, 10 last store issued, 11 exit;
-                     // 12 / 13 globaltimer at entry / exit, 14 SM id
+  long long* trace;
 #endif
   // epilogue
   const float* bias;
@@ -177,8 +178,11 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+#ifndef B200SR_GEMM_MIN_CTAS
+#define B200SR_GEMM_MIN_CTAS 1
+#endif
 template <int kCluster>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, B200SR_GEMM_MIN_CTAS)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -206,7 +210,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // per-CTA stage: 128 rows of A and this CTA's BN / kCluster rows of the weight tile
   const int b_sub_bytes = (p.BN / kCluster) * (BLOCK_K * 2);      // one 64-wide weight tile of this CTA
   const int b_stage_bytes = HALO_TAPS * b_sub_bytes;               // mode 3 weight-ring stage
-  const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);    // modes 0-2: [A0 | A1 | B0 | B1]
+  const int ksub = p.ksub;
+  const int stage_bytes = ksub * (A_STAGE_BYTES + b_sub_bytes);    // modes 0-2: [A0 | A1 | B0 | B1]
   const int stages = p.stages;
   const bool halo = p.mode == 3;
   const uint32_t rank = kCluster > 1 ? cluster_ctarank() : 0u;
@@ -223,6 +228,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_epi = reinterpret_cast<float*>(smem + ring_bytes + BAR_REGION_BYTES);  // [4 warps][256] staged bias
+  uint8_t* s_stage = smem + ring_bytes + BAR_REGION_BYTES + 4096;                 // [4 warps][2][32 rows x 80 B] transposes
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -245,10 +251,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1) {
     if (kCluster == 1) {
-      tmem_alloc(tmem_base_slot, TMEM_COLS);
+      tmem_alloc(tmem_base_slot, static_cast<uint32_t>(p.tmem_cols));
       tmem_relinquish();
     } else {
-      tmem2_alloc(tmem_base_slot, TMEM_COLS);
+      tmem2_alloc(tmem_base_slot, static_cast<uint32_t>(p.tmem_cols));
       tmem2_relinquish();
     }
   }
@@ -396,7 +402,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       const uint32_t sub_tx = static_cast<uint32_t>(A_STAGE_BYTES + b_sub_bytes) * kCluster;  // bytes of one K chunk, both CTAs
       const int b_rows = p.BN / kCluster;
-      const int s_iters = (p.k_iters + KSUB - 1) / KSUB;  // pipeline stages per tile
+      const int s_iters = (p.k_iters + ksub - 1) / ksub;  // pipeline stages per tile
       for (int work = work0; work < num_work; work += work_stride) {
         const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
         const int n_blk = work / m_groups;
@@ -427,13 +433,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const int st = w_only || a_only ? sit : stage;
           if (!w_only && !a_only) mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int nsub = p.k_iters - sit * KSUB < KSUB ? p.k_iters - sit * KSUB : KSUB;
+          const int nsub = p.k_iters - sit * ksub < ksub ? p.k_iters - sit * ksub : ksub;
           uint8_t* sa0 = smem + st * stage_bytes;
-          uint8_t* sb0 = sa0 + KSUB * A_STAGE_BYTES;
+          uint8_t* sb0 = sa0 + ksub * A_STAGE_BYTES;
           if (leader && !a_only) mbar_expect_tx(&full_bar[st], sub_tx * nsub);
           const uint32_t bar = kCluster > 1 ? mapa_cluster(smem_u32(&full_bar[st]), 0) : 0u;  // the leader's barrier
           for (int j = 0; j < nsub; ++j) {
-            const int kit = sit * KSUB + j;
+            const int kit = sit * ksub + j;
             uint8_t* sa = sa0 + j * A_STAGE_BYTES;
             uint8_t* sb = sb0 + j * b_sub_bytes;
             int kb;  // K coordinate of the weight tile
@@ -504,9 +510,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef B200SR_GEMM_TRACE
         const long long t_begin = clock64();
 #endif
-        const int s_iters = (p.k_iters + KSUB - 1) / KSUB;
+        const int s_iters = (p.k_iters + ksub - 1) / ksub;
         for (int it = 0; it < s_iters; ++it) {
-          const int nsub = p.k_iters - it * KSUB < KSUB ? p.k_iters - it * KSUB : KSUB;
+          const int nsub = p.k_iters - it * ksub < ksub ? p.k_iters - it * ksub : ksub;
 #ifdef B200SR_GEMM_TRACE
           n_chunks += nsub;
           if (!ready) {
@@ -525,7 +531,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ready = mbar_test_wait(&full_bar[ns], ns == 0 ? phase ^ 1 : phase);
           }
           const uint32_t sa0 = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb0 = sa0 + KSUB * A_STAGE_BYTES;
+          const uint32_t sb0 = sa0 + ksub * A_STAGE_BYTES;
           for (int j = 0; j < nsub; ++j) {
             const uint64_t adesc = umma_smem_desc_sw128(sa0 + j * A_STAGE_BYTES, 16, 1024);
             const uint64_t bdesc = umma_smem_desc_sw128(sb0 + j * b_sub_bytes, 16, 1024);
@@ -613,7 +619,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* rv_row = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
       uint4 res_cur[4], res_nxt[4];
       if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
-      if (has_res) {
+      if (has_res && (p.out_fp32 || p.geglu)) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
@@ -672,12 +678,45 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       uint32_t a_cur[32], a_nxt[32];
       if (p.softmax_valid <= 0) tmem_ld32(t_row, a_cur);
+      // bf16 outputs (everything but GEGLU / fp32 / softmax) go through a per-warp shared-memory transpose: the
+      // accumulator arrives one ROW per thread, so a direct store instruction would touch 32 different 128-byte lines
+      // for 16 bytes each (and a residual load likewise).  Staged, lane l moves 16 B of row 8i + l/4 (i = 0..3), piece
+      // l%4: 8 lines per instruction, 4x fewer LSU transactions — the epilogue of a one-tile-per-CTA GEMM is not
+      // overlapped with any mainloop, so its length is paid in full on every launch.
+      const bool staged = !p.out_fp32 && !p.geglu && p.softmax_valid <= 0;
+      uint8_t* st_res = s_stage + (warp - 2) * 5120;
+      uint8_t* st_out = st_res + 2560;
+      const int rsub = lane >> 2, piece = lane & 3;
+      long long crow[4];
+      bool cvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        crow[i] = __shfl_sync(0xffffffffu, row, 8 * i + rsub);
+        cvalid[i] = __shfl_sync(0xffffffffu, static_cast<int>(valid), 8 * i + rsub) != 0;
+      }
+      uint4 rc_cur[4], rc_nxt[4];
+      if (staged && p.residual != nullptr) {
+        // (overwrites the row-per-thread prefetch above: same bytes, coalesced)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rc_cur[i] = (cvalid[i] && n0 + piece * 8 < p.N)
+                          ? __ldg(reinterpret_cast<const uint4*>(p.residual + crow[i] * p.ldr + n0 + piece * 8))
+                          : make_uint4(0, 0, 0, 0);
+      }
       for (int c = 0; c < (p.softmax_valid > 0 ? 0 : p.BN); c += 32) {
         tmem_ld_wait();
         const bool more = c + 32 < p.BN;
         if (more) {
           tmem_ld32(t_row + c + 32, a_nxt);
-          if (has_res) {
+          if (staged) {
+            if (p.residual != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                rc_nxt[i] = (cvalid[i] && n0 + c + 32 + piece * 8 < p.N)
+                                ? __ldg(reinterpret_cast<const uint4*>(p.residual + crow[i] * p.ldr + n0 + c + 32 + piece * 8))
+                                : make_uint4(0, 0, 0, 0);
+            }
+          } else if (has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               res_nxt[q] = (n0 + c + 32 + q * 8 < p.N)
@@ -686,7 +725,80 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         const int col0 = n0 + c;
-        if (valid && col0 < p.N) {
+        if (staged) {
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(st_res + (8 * i + rsub) * 80 + piece * 16) = rc_cur[i];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res_cur[q] = *reinterpret_cast<const uint4*>(st_res + lane * 80 + q * 16);
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + j);
+            v[j] = __uint_as_float(a_cur[j]) + b4.x;
+            v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
+          }
+          if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          }
+          if (rv_row != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < p.N) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv_row + c + j));
+                v[j] += r4.x;
+                v[j + 1] += r4.y;
+                v[j + 2] += r4.z;
+                v[j + 3] += r4.w;
+              }
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f0 = unpack_bf16x2(res_cur[q].x), f1 = unpack_bf16x2(res_cur[q].y),
+                           f2 = unpack_bf16x2(res_cur[q].z), f3 = unpack_bf16x2(res_cur[q].w);
+              v[q * 8 + 0] += f0.x;
+              v[q * 8 + 1] += f0.y;
+              v[q * 8 + 2] += f1.x;
+              v[q * 8 + 3] += f1.y;
+              v[q * 8 + 4] += f2.x;
+              v[q * 8 + 5] += f2.y;
+              v[q * 8 + 6] += f3.x;
+              v[q * 8 + 7] += f3.y;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(st_out + lane * 80 + q * 16) = u;
+          }
+          __syncwarp();
+          if (col0 + piece * 8 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (cvalid[i]) {
+                const uint4 u = *reinterpret_cast<const uint4*>(st_out + (8 * i + rsub) * 80 + piece * 16);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + crow[i] * p.ldc + col0 + piece * 8) = u;
+              }
+            }
+          }
+          __syncwarp();
+        } else if (valid && col0 < p.N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -715,6 +827,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             reinterpret_cast<uint4*>(dst)[0] = q0;
             reinterpret_cast<uint4*>(dst)[1] = q1;
           } else {
+            // fp32 output (embedding projections): row-per-thread stores
             if (p.alpha != 1.0f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
@@ -750,26 +863,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             }
-            if (p.out_fp32) {
-              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
+            float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (col0 + q * 4 < p.N)
-                  reinterpret_cast<float4*>(dst)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              }
-            } else {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (col0 + q * 8 < p.N) {
-                  uint4 u;
-                  u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                  u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                  u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                  u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                  reinterpret_cast<uint4*>(dst)[q] = u;
-                }
-              }
+            for (int q = 0; q < 8; ++q) {
+              if (col0 + q * 4 < p.N)
+                reinterpret_cast<float4*>(dst)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
             }
           }
         }
@@ -777,7 +875,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) a_cur[j] = a_nxt[j];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) res_cur[q] = res_nxt[q];
+          for (int q = 0; q < 4; ++q) {
+            res_cur[q] = res_nxt[q];
+            rc_cur[q] = rc_nxt[q];
+          }
         }
       }
       // release this accumulator stage back to the MMA warp
@@ -803,9 +904,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   if (warp == 1) {
     if (kCluster == 1)
-      tmem_dealloc(tmem_base, TMEM_COLS);
+      tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
     else
-      tmem2_dealloc(tmem_base, TMEM_COLS);
+      tmem2_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 #ifdef B200SR_GEMM_TRACE
   if (threadIdx.x == 0 && p.trace != nullptr) {
@@ -855,11 +956,34 @@ static int pick_bn(int m_blocks, int N, int k_iters, int sms, int cluster) {
 static long long* g_gemm_trace = nullptr;
 #endif
 
+// B200SR_GEMM_COOP (default 1): launches in which every CTA owns a single tile (the M = 2048 GEMMs of the step: 64 tiles
+// on 74 CTA-pair slots) take half of the shared memory (<= 112 KB ring) and only the TMEM columns of ONE accumulator,
+// so that the CTAs of the next kernel in the stream — launched early through programmatic dependent launch — are
+// resident beside them: their barrier / TMEM / descriptor prologue and their weight prefetch then overlap this
+// kernel's epilogue instead of following it.  B200SR_GEMM_COOP=0 restores one resident CTA per SM.
+static bool gemm_coop_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200SR_GEMM_COOP");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/;
+  const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
+  const int slots = num_sms() / kCluster;
+  const bool single = work <= slots && p.mode != 3 && gemm_coop_enabled();
+  const int fixed_bytes = 1024 /*align slack*/ + BAR_REGION_BYTES + 4096 /*epilogue bias staging*/ + EPI_STAGE_BYTES;
+  const int smem_budget = (single ? 113 * 1024 : 227 * 1024) - fixed_bytes;
   const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
-  const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
+  p.tmem_cols = TMEM_COLS;
+  if (single) {
+    int c = 32;
+    while (c < p.BN) c *= 2;
+    p.tmem_cols = c;
+  }
   size_t ring_bytes;
   if (p.mode == 3) {
     const int b_stage_bytes = HALO_TAPS * b_sub_bytes;
@@ -868,9 +992,14 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
     if (stages > MAX_B_STAGES) stages = MAX_B_STAGES;
     if (stages < 2) return B200SR_EINVAL;
     p.stages = stages;
+    p.ksub = KSUB;
     ring_bytes = static_cast<size_t>(p.a_stages) * A_HALO_BYTES + static_cast<size_t>(stages) * b_stage_bytes;
   } else {
-    const int s_iters = (p.k_iters + KSUB - 1) / KSUB;
+    // two K chunks per stage when at least three such stages fit; one chunk per stage under the halved budget
+    p.ksub = KSUB;
+    if (smem_budget / (p.ksub * (A_STAGE_BYTES + b_sub_bytes)) < 3) p.ksub = 1;
+    const int stage_bytes = p.ksub * (A_STAGE_BYTES + b_sub_bytes);
+    const int s_iters = (p.k_iters + p.ksub - 1) / p.ksub;
     int stages = smem_budget / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > s_iters + 1) stages = s_iters + 1;
@@ -879,7 +1008,8 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
     p.a_stages = 0;
     ring_bytes = static_cast<size_t>(stages) * stage_bytes;
   }
-  const size_t smem_bytes = ring_bytes + 1024 + BAR_REGION_BYTES + 4096;
+  const size_t smem_bytes = ring_bytes + fixed_bytes;
+  if (smem_bytes > 227 * 1024) return B200SR_EINVAL;
 #ifdef B200SR_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
@@ -889,8 +1019,6 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
         cudaSuccess)
       return B200SR_ELAUNCH;
   }
-  const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
-  const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
   const cudaError_t err = launch_k(gemm_conv_kernel<kCluster>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream,
                                    kCluster, tmA, tmB, p);

@@ -37,6 +37,7 @@
 // per-row-group weights (per-batch-element B operands), bf16 or fp32 output.
 #include "common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace b200sr {
 
@@ -80,6 +81,7 @@ struct GemmParams {
   int tiles_w, tiles_h, tiles_n;
   int stages;
   int a_stages;  // mode 3: halo-tile ring depth (stages = weight ring depth)
+  int epi_tma;   // mode 0, bf16 output, one tile per CTA: residual arrives and the result leaves through TMA (see epilogue)
 #ifdef B200SR_GEMM_TRACE
   long long* trace;  // [grid][16]: 0 mainloop cycles, 1 cycles blocked on the full barrier, 2 chunks, 3 chunks found not ready,
                      // clock64 stamps: 4 entry, 5 set-up done, 6 producer past griddepcontrol.wait, 7 first stage landed,
@@ -180,7 +182,7 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
 template <int kCluster>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Round the dynamic smem base up to 1024 B (swizzle-128B atoms are 1024 B aligned).  The
   // offset is identical in both CTAs of a cluster (same kernel, same static layout), which the
@@ -222,7 +224,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = a_empty + MAX_A_HALO_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(tmem_base_slot + 2);          // epi_tma: residual tile landed
   float* s_epi = reinterpret_cast<float*>(smem + ring_bytes + BAR_REGION_BYTES);  // [4 warps][256] staged bias
+  // epi_tma: [4 warps][BN / 32 chunks][32 rows x 64 B] output tile (64-byte swizzle), pre-filled with the residual
+  uint8_t* s_ctile = smem + ring_bytes + BAR_REGION_BYTES + 4096;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -240,6 +245,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4 * kCluster);  // one arrive per epilogue warp of every CTA in the pair
+    }
+    mbar_init(res_full, 1);
+    if (p.epi_tma) {
+      tma_prefetch_desc(&tmO);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmR);
     }
     fence_barrier_init();
   }
@@ -424,6 +434,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (it == pre && first) {
             pdl_wait();
             GT(6);
+            if (p.epi_tma && p.residual != nullptr) {
+              // The whole residual tile of this CTA (128 rows x BN columns) as 32 x 32 boxes, one per (epilogue warp,
+              // column chunk), into the shared-memory tile the epilogue later overwrites in place and stores from.
+              // It travels while the mainloop runs; out-of-range rows / columns are zero-filled.
+              const int nchunks = p.BN / 32;
+              mbar_expect_tx(res_full, static_cast<uint32_t>(4 * nchunks * 2048));
+              for (int w = 0; w < 4; ++w)
+                for (int c = 0; c < nchunks; ++c)
+                  tma_load_2d(s_ctile + (w * nchunks + c) * 2048, &tmR, res_full, n_blk * p.BN + c * 32,
+                              m_blk * BLOCK_M + w * 32);
+            }
           }
           const int st = w_only || a_only ? sit : stage;
           if (!w_only && !a_only) mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -613,7 +634,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* rv_row = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
       uint4 res_cur[4], res_nxt[4];
       if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
-      if (has_res) {
+      if (has_res && !p.epi_tma) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
@@ -670,9 +691,90 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (p.epi_tma) {
+        // One tile per CTA, so nothing overlaps this epilogue: it is kept off the LSU / L2 request path.  The residual
+        // tile is already in shared memory (TMA, during the mainloop); each thread adds its row of a 32-column chunk in
+        // place (64-byte-swizzled rows: conflict-free 16-byte accesses) and one lane per warp hands the finished
+        // 32 x 32 box to a TMA store: full-line writes, rows / columns beyond M / N clipped by the tensor map.
+        const int nchunks = p.BN / 32;
+        uint8_t* tile = s_ctile + sub * nchunks * 2048;   // slab `sub` holds accumulator rows [32 sub, 32 sub + 32)
+        const bool with_res = p.residual != nullptr;
+        if (with_res) mbar_wait(res_full, 0);
+        uint32_t a_cur[32], a_nxt[32];
+        tmem_ld32(t_row, a_cur);
+        const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);   // 64B swizzle: 16-byte chunk index ^ bits [7:8] of the offset
+        for (int c = 0; c < p.BN; c += 32) {
+          tmem_ld_wait();
+          if (c + 32 < p.BN) tmem_ld32(t_row + c + 32, a_nxt);
+          uint8_t* rowp = tile + (c >> 5) * 2048 + lane * 64;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + j);
+            v[j] = __uint_as_float(a_cur[j]) + b4.x;
+            v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
+          }
+          if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          }
+          if (rv_row != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + c + j < p.N) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv_row + c + j));
+                v[j] += r4.x;
+                v[j + 1] += r4.y;
+                v[j + 2] += r4.z;
+                v[j + 3] += r4.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4* slot = reinterpret_cast<uint4*>(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
+            if (with_res) {
+              const uint4 rr = *slot;
+              const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y), f2 = unpack_bf16x2(rr.z),
+                           f3 = unpack_bf16x2(rr.w);
+              v[q * 8 + 0] += f0.x;
+              v[q * 8 + 1] += f0.y;
+              v[q * 8 + 2] += f1.x;
+              v[q * 8 + 3] += f1.y;
+              v[q * 8 + 4] += f2.x;
+              v[q * 8 + 5] += f2.y;
+              v[q * 8 + 6] += f3.x;
+              v[q * 8 + 7] += f3.y;
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[q * 8 + j] = silu_f(v[q * 8 + j]);
+            }
+            uint4 u;
+            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            *slot = u;
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy) read below
+          __syncwarp();
+          if (lane == 0 && n0 + c < p.N) {
+            tma_store_2d(&tmO, tile + (c >> 5) * 2048, n0 + c, m_blk * BLOCK_M + sub * 32);
+            tma_store_commit();
+          }
+          if (c + 32 < p.BN) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a_cur[j] = a_nxt[j];
+          }
+        }
+        if (lane == 0) tma_store_wait_all();   // results complete (and the tile no longer read) before the CTA winds down
+      }
       uint32_t a_cur[32], a_nxt[32];
-      if (p.softmax_valid <= 0) tmem_ld32(t_row, a_cur);
-      for (int c = 0; c < (p.softmax_valid > 0 ? 0 : p.BN); c += 32) {
+      if (p.softmax_valid <= 0 && !p.epi_tma) tmem_ld32(t_row, a_cur);
+      for (int c = 0; c < ((p.softmax_valid > 0 || p.epi_tma) ? 0 : p.BN); c += 32) {
         tmem_ld_wait();
         const bool more = c + 32 < p.BN;
         if (more) {
@@ -855,9 +957,28 @@ static int pick_bn(int m_blocks, int N, int k_iters, int sms, int cluster) {
 static long long* g_gemm_trace = nullptr;
 #endif
 
+// B200SR_GEMM_EPI_TMA=0 keeps the register / LSU epilogue everywhere (A/B measurements).
+static bool epi_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200SR_GEMM_EPI_TMA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/;
+  const int work_units = (p.num_m_blocks / kCluster) * p.num_n_blocks;
+  // TMA epilogue: plain GEMM, bf16 result, every CTA owns one tile (its epilogue is then fully exposed), 16-byte aligned
+  // rows; the staged tile takes BN x 256 B of shared memory next to the ring.
+  p.epi_tma = (p.mode == 0 && !p.out_fp32 && !p.geglu && p.softmax_valid <= 0 && work_units <= num_sms() / kCluster &&
+               (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+               (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && epi_tma_enabled())
+                  ? 1
+                  : 0;
+  const int ctile_bytes = p.epi_tma ? p.BN * 256 : 0;
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/ - ctile_bytes;
   const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
   const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
   size_t ring_bytes;
@@ -879,7 +1000,22 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
     p.a_stages = 0;
     ring_bytes = static_cast<size_t>(stages) * stage_bytes;
   }
-  const size_t smem_bytes = ring_bytes + 1024 + BAR_REGION_BYTES + 4096;
+  const size_t smem_bytes = ring_bytes + 1024 + BAR_REGION_BYTES + 4096 + ctile_bytes;
+  // ring stages are multiples of 1 KiB and the barrier + bias regions 4.5 KiB, so the tile starts 512-byte aligned
+  CUtensorMap tmR, tmO;
+  memset(&tmR, 0, sizeof(tmR));
+  memset(&tmO, 0, sizeof(tmO));
+  if (p.epi_tma) {
+    uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+    uint32_t box[2] = {32, 32};
+    uint64_t so[1] = {static_cast<uint64_t>(p.ldc) * 2};
+    int rc = make_tmap_bf16(&tmO, p.out, 2, dims, so, box, 64);
+    if (rc == B200SR_OK && p.residual != nullptr) {
+      uint64_t sr[1] = {static_cast<uint64_t>(p.ldr) * 2};
+      rc = make_tmap_bf16(&tmR, p.residual, 2, dims, sr, box, 64);
+    }
+    if (rc) return rc;
+  }
 #ifdef B200SR_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
@@ -893,7 +1029,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
   const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
   const cudaError_t err = launch_k(gemm_conv_kernel<kCluster>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream,
-                                   kCluster, tmA, tmB, p);
+                                   kCluster, tmA, tmB, tmR, tmO, p);
   return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

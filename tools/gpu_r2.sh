@@ -18,7 +18,7 @@ print('ms/step', d['ms_per_step'], 'steps/s', d['value'], 'e2e', d['e2e']['value
 r = d['roofline']; print('dense achieved', r['achieved'], 'frac', r['frac'], 'share', r['share_of_step_time'], 'eager ms', r['eager_step_ms'])
 for k, v in r['by_kind'].items(): print(' ', k, v)
 print('clocks', d['clocks'])
-for k in ('cpu_baseline', 'gpu_eager_baseline', 'tiled_x8', 'images_per_s'):
+for k in ('cpu_baseline', 'gpu_eager_baseline', 'batched', 'tiled_x8', 'images_per_s'):
     print(k, json.dumps(d.get(k)))
 PY
 fi
