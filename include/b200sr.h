@@ -49,7 +49,8 @@ typedef struct b200sr_epilogue {
   int32_t out_fp32;
   int32_t geglu;
   float alpha;
-  int32_t act;              /* 0 = none, 1 = SiLU applied to the final value (ZeroSFT mlp_shared, SR_modules.py:75-78) */
+  int32_t act;              /* applied to the final value: 0 = none, 1 = SiLU (ZeroSFT mlp_shared, SR_modules.py:75-78),
+                               2 = GELU (erf; open_clip text tower MLP), 3 = quick GELU x*sigmoid(1.702x) (CLIP-L text tower) */
   /* Cross-attention against a context that is constant over the sampler steps (the text embedding,
    * attention.py:222-285), with to_q folded into the keys and to_out into the values:
    *   P = softmax_per_head(x K'^T)   one GEMM, N = heads * 80, epilogue = softmax over each 80-column
@@ -115,11 +116,13 @@ int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* 
  * workspace: b200sr_attention_d64_workspace_bytes() bytes of device scratch (NULL allowed when that is
  * 0).  The tiles of the last, partial wave of CTAs are split over the key range and merged through
  * it; its first 2 KiB are arrival counters: zero them once after allocation, every call leaves them
- * zeroed.  Calls that may run concurrently (different streams) need distinct workspaces.       */
+ * zeroed.  Calls that may run concurrently (different streams) need distinct workspaces.
+ * causal != 0 (Nq == Nk <= 128): key k takes part in query q only if k <= q — the text towers of the conditioner
+ * (transformers CLIPTextModel / open_clip attn_mask, sgm/modules/encoders/modules.py:436-613).    */
 size_t b200sr_attention_d64_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t Nk);
 int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
-                         int32_t Nq, int32_t Nk, float scale, void* workspace, void* stream);
+                         int32_t Nq, int32_t Nk, float scale, int32_t causal, void* workspace, void* stream);
 
 /* y = softmax(x * scale) over the first valid_cols entries of each row (the rest are written as 0: zero-
  * padded keys); x fp32 [rows, cols], y bf16.  SR3 SelfAttention (one head of width C, scores from
@@ -148,6 +151,11 @@ int b200sr_pad_channels(const void* x, void* y, int32_t C, int32_t Cpad, int64_t
 
 /* y = silu(x), bf16 (embedding path: openaimodel.py:281-283, :660-662). */
 int b200sr_silu_bf16(const void* x, void* y, int64_t n, void* stream);
+
+/* out[b, t, :] = tok[ids[b, t], :] + pos[t, :] (fp32 tables, int64 ids, bf16 out): token + position embedding of
+ * the conditioner's text towers (sgm/modules/encoders/modules.py:473-493, :569-571). */
+int b200sr_embed_tokens(const int64_t* ids, const float* tok, const float* pos, void* out, int32_t B, int32_t T, int32_t C,
+                        int32_t vocab, void* stream);
 
 /* Sinusoidal embedding of t[B] (fp32) to bf16 [B, dim]; sin_first = 0: cos|sin (util.py:206-230),
  * sin_first = 1: sin|cos (sr3 unet.py:19-32).                                                 */

@@ -203,6 +203,79 @@ def colorfix(size=48):
     print("[colorfix] wrote golden")
 
 
+def conditioner(clip_layers=3, clip_idx=2, bigg_layers=3):
+    """Text towers at reduced depth (full widths): the installed transformers implementation vs oracle/conditioner.py."""
+    import transformers
+    from oracle import conditioner as ocond
+
+    sys.path.insert(0, os.path.join(ROOT, "remote-sensing-vision-language-diffusion-model_b200"))
+    from b200sr import conditioner as pcond   # parameter containers only (names / shapes of the reference's modules)
+
+    m = pcond.GeneralConditionerWithControl(_clip_layers=clip_layers, _clip_layer_idx=clip_idx, _bigg_layers=bigg_layers)
+    sd = weights.fill_(m.state_dict(), 0)
+    g = torch.Generator().manual_seed(23)
+    ids = torch.randint(1, 49000, (2, 77), generator=g)
+    ids[0, 20], ids[1, 33] = 49407, 49407           # eot = highest id
+    ids[0, 21:], ids[1, 34:] = 0, 0
+    # CLIP-L: transformers.CLIPTextModel
+    cfg = transformers.CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=clip_layers,
+                                      num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu",
+                                      eos_token_id=2, bos_token_id=0, pad_token_id=1)
+    hf = transformers.CLIPTextModel(cfg).eval()
+    pre = "embedders.0.transformer."
+    missing = hf.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
+    with torch.no_grad():
+        ref_l = hf(input_ids=ids, output_hidden_states=True).hidden_states[clip_idx]
+        or_l = ocond.clip_l_hidden_states(sd, pre + "text_model.", ids)[clip_idx]
+    print(f"[conditioner] CLIP-L hidden[{clip_idx}] |ref|max {ref_l.abs().max():.3f} oracle-vs-transformers {maxdiff(ref_l, or_l):.3e}")
+    assert maxdiff(ref_l, or_l) < 1e-4 * max(1.0, ref_l.abs().max().item())
+    # bigG text tower: transformers.CLIPTextModelWithProjection with the open_clip weights re-laid-out
+    cfg2 = transformers.CLIPTextConfig(vocab_size=49408, hidden_size=1280, intermediate_size=5120, num_hidden_layers=bigg_layers,
+                                       num_attention_heads=20, max_position_embeddings=77, hidden_act="gelu",
+                                       projection_dim=1280, eos_token_id=2, bos_token_id=0, pad_token_id=1)
+    hf2 = transformers.CLIPTextModelWithProjection(cfg2).eval()
+    q = "embedders.1.model."
+    m2 = {"text_model.embeddings.token_embedding.weight": sd[q + "token_embedding.weight"],
+          "text_model.embeddings.position_embedding.weight": sd[q + "positional_embedding"],
+          "text_model.final_layer_norm.weight": sd[q + "ln_final.weight"], "text_model.final_layer_norm.bias": sd[q + "ln_final.bias"],
+          "text_projection.weight": sd[q + "text_projection"].t().contiguous()}
+    for i in range(bigg_layers):
+        r, t = f"{q}transformer.resblocks.{i}.", f"text_model.encoder.layers.{i}."
+        wq, wk, wv = sd[r + "attn.in_proj_weight"].chunk(3, 0)
+        bq, bk, bv = sd[r + "attn.in_proj_bias"].chunk(3, 0)
+        m2.update({t + "self_attn.q_proj.weight": wq, t + "self_attn.k_proj.weight": wk, t + "self_attn.v_proj.weight": wv,
+                   t + "self_attn.q_proj.bias": bq, t + "self_attn.k_proj.bias": bk, t + "self_attn.v_proj.bias": bv,
+                   t + "self_attn.out_proj.weight": sd[r + "attn.out_proj.weight"], t + "self_attn.out_proj.bias": sd[r + "attn.out_proj.bias"],
+                   t + "layer_norm1.weight": sd[r + "ln_1.weight"], t + "layer_norm1.bias": sd[r + "ln_1.bias"],
+                   t + "layer_norm2.weight": sd[r + "ln_2.weight"], t + "layer_norm2.bias": sd[r + "ln_2.bias"],
+                   t + "mlp.fc1.weight": sd[r + "mlp.c_fc.weight"], t + "mlp.fc1.bias": sd[r + "mlp.c_fc.bias"],
+                   t + "mlp.fc2.weight": sd[r + "mlp.c_proj.weight"], t + "mlp.fc2.bias": sd[r + "mlp.c_proj.bias"]})
+    missing = hf2.load_state_dict(m2, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
+    with torch.no_grad():
+        o2 = hf2(input_ids=ids, output_hidden_states=True)
+        ref_pen, ref_pool = o2.hidden_states[-2], o2.text_embeds
+        or_pen, or_pool = ocond.openclip_text(sd, q, ids)
+    print(f"[conditioner] bigG penultimate oracle-vs-transformers {maxdiff(ref_pen, or_pen):.3e}; pooled {maxdiff(ref_pool, or_pool):.3e}")
+    assert maxdiff(ref_pen, or_pen) < 1e-4 * max(1.0, ref_pen.abs().max().item())
+    assert maxdiff(ref_pool, or_pool) < 1e-4 * max(1.0, ref_pool.abs().max().item())
+    batch = {"txt": (ids, ids.flip(0)), "original_size_as_tuple": torch.tensor([[1024., 1024.]] * 2),
+             "crop_coords_top_left": torch.zeros(2, 2), "target_size_as_tuple": torch.tensor([[1024., 1024.]] * 2)}
+    with torch.no_grad():
+        out = ocond.conditioner(sd, batch, clip_idx)
+    # the size embedders against sgm's own Timestep module
+    reference_import.install_stubs()
+    from sgm.modules.diffusionmodules.openaimodel import Timestep
+    ts = Timestep(256)(torch.tensor([1024., 1024., 0., 0.]))
+    assert maxdiff(ts.reshape(2, 512), torch.stack([ocond.concat_timestep(torch.tensor([[1024., 1024.]]))[0],
+                                                    ocond.concat_timestep(torch.zeros(1, 2))[0]])) < 1e-6
+    torch.save({"clip_layers": clip_layers, "clip_idx": clip_idx, "bigg_layers": bigg_layers, "ids": ids,
+                "clip_hidden": ref_l, "bigg_penultimate": ref_pen, "bigg_pooled": ref_pool,
+                "crossattn": out["crossattn"], "vector": out["vector"]}, os.path.join(GOLDEN, "conditioner_small.pt"))
+    print("[conditioner] wrote golden")
+
+
 def tables():
     reference_import.install_stubs()
     from sgm.modules.diffusionmodules.sampling import _sliding_windows
@@ -254,6 +327,9 @@ if __name__ == "__main__":
     if "--vae-only" in sys.argv:
         vae()
         sys.exit(0)
+    if "--conditioner-only" in sys.argv:
+        conditioner()
+        sys.exit(0)
     if "--colorfix-only" in sys.argv:
         colorfix()
         sys.exit(0)
@@ -261,4 +337,5 @@ if __name__ == "__main__":
     sr3()
     vae()
     colorfix()
+    conditioner()
     stage2()

@@ -22,7 +22,8 @@ import torch
 # unavoidable bf16 operand rounding of every layer to ~1e-2 on its own, leaving no room to judge the
 # kernels).  The SR3 residual ends (block2 conv, attention out conv) get the same treatment.
 BRANCH_END = (".out_layers.3.", ".proj_out.", ".zero_mul.", ".zero_add.", ".zero_conv.", ".input_hint_block.0.",
-              ".out.2.", ".block2.block.3.", ".attn.out.", ".conv2.")   # .conv2. = the first stage's ResnetBlock branch end
+              ".out.2.", ".block2.block.3.", ".attn.out.", ".conv2.",   # .conv2. = the first stage's ResnetBlock branch end
+              ".out_proj.", ".fc2.", ".c_proj.")                        # text towers: attention / MLP output projections
 BRANCH_END_GAIN = 0.25
 
 
@@ -38,7 +39,7 @@ def fill_(sd: Dict[str, torch.Tensor], seed: int = 0) -> Dict[str, torch.Tensor]
         leaf = name.rsplit(".", 1)[-1]
         dotted = "." + name
         is_norm = t.dim() == 1 and any(
-            s in dotted for s in ("norm", ".in_layers.0.", ".out_layers.0.", ".out.0.", ".block.0."))   # incl. norm1/norm2/norm_out
+            s in dotted for s in ("norm", ".in_layers.0.", ".out_layers.0.", ".out.0.", ".block.0.", ".ln_"))   # incl. norm1/norm2/norm_out, ln_1/ln_2/ln_final
         if is_norm:
             r = r * 0.05 + (1.0 if leaf == "weight" else 0.0)
         elif t.dim() >= 2:

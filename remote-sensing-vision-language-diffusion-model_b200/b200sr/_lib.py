@@ -80,7 +80,7 @@ SIGNATURES = {
     "b200sr_layer_norm": (c_int, [P, P, P, P, c_int, c_int, c_float, P]),
     "b200sr_attention_d64": (
         c_int,
-        [P, c_i64, c_int, P, c_i64, c_int, P, c_i64, c_int, P, c_i64, c_int, c_int, c_int, c_int, c_float, P, P],
+        [P, c_i64, c_int, P, c_i64, c_int, P, c_i64, c_int, P, c_i64, c_int, c_int, c_int, c_int, c_float, c_int, P, P],
     ),
     "b200sr_attention_d64_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int, c_int]),
     "b200sr_softmax_rows": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
@@ -91,6 +91,7 @@ SIGNATURES = {
     "b200sr_axpy_bf16": (c_int, [P, P, P, c_float, c_i64, P]),
     "b200sr_silu_bf16": (c_int, [P, P, c_i64, P]),
     "b200sr_pad_channels": (c_int, [P, P, c_int, c_int, c_i64, P]),
+    "b200sr_embed_tokens": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "b200sr_sinusoid_embedding": (c_int, [P, P, c_int, c_int, c_float, c_int, P]),
     "b200sr_sampler_pre": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "b200sr_sampler_post": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),

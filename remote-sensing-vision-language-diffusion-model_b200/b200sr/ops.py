@@ -351,7 +351,7 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
 # ------------------------------------------------------------------------------------------------
 def attention(
     q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, q_col: int = 0, k_col: int = 0, v_col: int = 0,
-    scale: Optional[float] = None
+    scale: Optional[float] = None, causal: bool = False
 ) -> torch.Tensor:
     """q: [B, Nq, ldq], k / v: [B, Nk, ld] row-major bf16 matrices; head h of q occupies columns
     [q_col + 64h, q_col + 64h + 64) (likewise k_col / v_col) so a fused QKV buffer can be passed
@@ -367,7 +367,7 @@ def attention(
     with _Timed("attention", 4.0 * b * heads * nq * nk * 64, f"B{b} H{heads} Nq{nq} Nk{nk}"):
         rc = lib.b200sr_attention_d64(
             q.data_ptr(), ldq, q_col, k.data_ptr(), k.shape[2], k_col, v.data_ptr(), v.shape[2], v_col, out.data_ptr(),
-            heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), _ptr(ws), _stream()
+            heads * 64, b, heads, nq, nk, float(scale if scale is not None else 0.125), int(causal), _ptr(ws), _stream()
         )
     check(rc, f"attention B={b} H={heads} Nq={nq} Nk={nk}")
     return out
@@ -516,6 +516,19 @@ def silu(x: torch.Tensor) -> torch.Tensor:
     y = torch.empty_like(x)
     check(_lib.load().b200sr_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu")
     return y
+
+
+def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """tok[ids] + pos: ids int64 [B, T], tok fp32 [vocab, C], pos fp32 [T, C] -> bf16 [B, T, C]."""
+    _req(ids, torch.int64, "embed_tokens.ids")
+    _req(tok, torch.float32, "embed_tokens.tok")
+    _req(pos, torch.float32, "embed_tokens.pos")
+    b, t = ids.shape
+    c = tok.shape[1]
+    out = torch.empty(b, t, c, dtype=bf16, device=ids.device)
+    check(_lib.load().b200sr_embed_tokens(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), out.data_ptr(), b, t, c, tok.shape[0],
+                                          _stream()), "embed_tokens")
+    return out
 
 
 def sinusoid_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0, sin_first: bool = False) -> torch.Tensor:

@@ -42,6 +42,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long ldo;  // elements per output row ([B*Nq, ldo], head h at columns h*64)
   float scale_log2;  // softmax scale * log2(e)
+  int causal;        // != 0: key k takes part in query q only if k <= q (text towers of the conditioner)
   // Tail splitting (see attention_plan): CTAs [0, full_ctas) each own a whole 128-row tile; the
   // remaining tiles are each shared by `split` CTAs that take `blocks_per_split` key blocks apiece,
   // publish (O, m, l) partials to `partials` and the last to arrive merges them.
@@ -259,7 +260,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       tmem_ld_wait();
       ATT_T(1);
-      const int kv_left = p.Nk - (jb0 + j) * ATT_BN - half * 64;
+      int kv_left = p.Nk - (jb0 + j) * ATT_BN - half * 64;
+      if (p.causal) kv_left = min(kv_left, q0 + r + 1 - (jb0 + j) * ATT_BN - half * 64);   // keys 0 .. q only
       if (kv_left < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -447,8 +449,9 @@ size_t attention_d64_workspace_bytes(int B, int H, int Nq, int Nk) {
 // arrival counters that must be zero before the first call and are left zero by every call.
 int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
                   long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
-                  void* workspace, cudaStream_t stream) {
+                  int causal, void* workspace, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return B200SR_EINVAL;
+  if (causal && (Nq != Nk || Nk > ATT_BN)) return B200SR_EINVAL;   // causal: self-attention within one key block (77 tokens)
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (q_col % 8) || (k_col % 8) || (v_col % 8))
     return B200SR_EINVAL;
   if (q_col + H * ATT_D > ldq || k_col + H * ATT_D > ldk || v_col + H * ATT_D > ldv || H * ATT_D > ldo)
@@ -473,6 +476,7 @@ int attention_d64(const void* q, long long ldq, int q_col, const void* k, long l
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
   p.n_qtiles = plan.n_qtiles;
   p.full_ctas = plan.full;
   p.split = plan.split;

@@ -94,7 +94,9 @@ int layer_norm(const void* x, void* y, const float* weight, const float* bias, i
 int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream);
 int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
                   long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
-                  void* workspace, cudaStream_t stream);
+                  int causal, void* workspace, cudaStream_t stream);
+int embed_tokens(const long long* ids, const float* tok, const float* pos, void* out, int B, int T, int C, int vocab,
+                 cudaStream_t stream);
 size_t attention_d64_workspace_bytes(int B, int H, int Nq, int Nk);
 int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int HW, float scale, cudaStream_t stream);
 int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStream_t stream);
@@ -214,10 +216,15 @@ int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int
 }
 int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
-                         int32_t Nq, int32_t Nk, float scale, void* workspace, void* stream) {
+                         int32_t Nq, int32_t Nk, float scale, int32_t causal, void* workspace, void* stream) {
   if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return B200SR_EINVAL;
-  return attention_d64(q, ldq, q_col, k, ldk, k_col, v, ldv, v_col, out, ldo, B, H, Nq, Nk, scale, workspace,
+  return attention_d64(q, ldq, q_col, k, ldk, k_col, v, ldv, v_col, out, ldo, B, H, Nq, Nk, scale, causal, workspace,
                        S(stream));
+}
+int b200sr_embed_tokens(const int64_t* ids, const float* tok, const float* pos, void* out, int32_t B, int32_t T, int32_t C,
+                        int32_t vocab, void* stream) {
+  if (ids == nullptr || tok == nullptr || pos == nullptr || out == nullptr) return B200SR_EINVAL;
+  return embed_tokens(reinterpret_cast<const long long*>(ids), tok, pos, out, B, T, C, vocab, S(stream));
 }
 size_t b200sr_attention_d64_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t Nk) {
   return attention_d64_workspace_bytes(B, H, Nq, Nk);

@@ -262,6 +262,13 @@ __device__ __forceinline__ float silu_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
 }
+// x * sigmoid(1.702 x): the "quick_gelu" of the CLIP-L text tower (transformers' CLIPTextModel, hidden_act = quick_gelu).
+__device__ __forceinline__ float quick_gelu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (-1.702f * 1.4426950408889634f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 // Exact (erf) GELU, attention.py:84-91 via F.gelu.  erf by Abramowitz & Stegun 7.1.28,
 //   erf(t) = 1 - (1 + a1 t + ... + a6 t^6)^-16,  |error| <= 3e-7 for t >= 0,
 // branch-free and 11 instructions shorter than erff(): the GEGLU GEMM is bound by its epilogue's
@@ -361,7 +368,7 @@ struct EpilogueArgs {
   int out_fp32;
   int geglu;
   float alpha;
-  int act;  // 0 = none, 1 = SiLU (applied last)
+  int act;  // 0 = none, 1 = SiLU, 2 = GELU (erf), 3 = quick GELU (applied last)
   int softmax_valid;        // > 0: epilogue = row softmax over each 80-column segment (first softmax_valid columns)
   int w_dynamic;            // != 0: the W operand is produced by an earlier kernel (no prefetch ahead of griddepcontrol.wait)
   int w_rows_per_group;     // > 0: rows [g * w_rows_per_group, ...) of A use weight rows offset by g * w_group_stride

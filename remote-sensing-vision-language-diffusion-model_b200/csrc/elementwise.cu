@@ -821,4 +821,35 @@ int diag_gaussian(const float* moments, const float* noise, float* z, int N, int
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
+// ------------------------------------------------------------------------------------------
+// Token + position embedding of the text towers (transformers CLIPTextEmbeddings; open_clip
+// model.token_embedding(text) + model.positional_embedding, sgm/modules/encoders/modules.py:569-571):
+//   out[b, t, :] = tok[ids[b, t], :] + pos[t, :]      fp32 tables -> bf16 tokens
+// ------------------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
+                                    const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int T, int C,
+                                    int vocab, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t bt = i / C;
+    const int t = static_cast<int>(bt % T);
+    long long id = ids[bt];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    out[i] = __float2bfloat16(tok[static_cast<size_t>(id) * C + c] + pos[static_cast<size_t>(t) * C + c]);
+  }
+}
+int embed_tokens(const long long* ids, const float* tok, const float* pos, void* out, int B, int T, int C, int vocab,
+                 cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || C <= 0 || vocab <= 0) return B200SR_EINVAL;
+  const size_t total = static_cast<size_t>(B) * T * C;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  launch_k(embed_tokens_kernel, dim3(grid), dim3(256), 0, stream, 1, ids, tok, pos, reinterpret_cast<__nv_bfloat16*>(out), T, C,
+           vocab, total);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
 }  // namespace b200sr

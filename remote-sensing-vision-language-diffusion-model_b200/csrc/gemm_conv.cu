@@ -749,6 +749,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if (p.act == 2) {   // exact (erf) GELU: OpenCLIP text tower MLP
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+            } else if (p.act == 3) {   // quick GELU x * sigmoid(1.702 x): CLIP-L text tower MLP
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = quick_gelu_f(v[j]);
             }
             if (p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
@@ -921,6 +927,7 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
     return B200SR_EINVAL;
   if (e.w_rows_per_group < 0 || (e.w_rows_per_group % (2 * BLOCK_M)) != 0) return B200SR_EINVAL;
   if (e.geglu && e.act) return B200SR_EINVAL;
+  if (e.act < 0 || e.act > 3) return B200SR_EINVAL;
   if (e.out == nullptr) return B200SR_EINVAL;
   if (e.geglu && (e.out_fp32 || e.residual != nullptr || e.rowvec != nullptr || (p.N % 32) != 0)) return B200SR_EINVAL;
   if (p.N % 8 != 0) return B200SR_EINVAL;

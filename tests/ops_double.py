@@ -48,6 +48,10 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu
             y = y + residual.float().reshape(-1, residual.shape[-1])
         if act == 1:
             y = F.silu(y)
+        elif act == 2:
+            y = F.gelu(y)
+        elif act == 3:
+            y = y * torch.sigmoid(1.702 * y)
     y = y.reshape(*a.shape[:-1], y.shape[-1])
     y = y if out_fp32 else y.to(bf16)
     if out is not None:
@@ -114,13 +118,16 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return F.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps).to(bf16)
 
 
-def attention(q, k, v, heads, *, q_col=0, k_col=0, v_col=0, scale=None):
+def attention(q, k, v, heads, *, q_col=0, k_col=0, v_col=0, scale=None, causal=False):
     b, nq, _ = q.shape
     c = heads * 64
     qf = q.float()[..., q_col:q_col + c].reshape(b, nq, heads, 64).transpose(1, 2)
     kf = k.float()[..., k_col:k_col + c].reshape(b, -1, heads, 64).transpose(1, 2)
     vf = v.float()[..., v_col:v_col + c].reshape(b, -1, heads, 64).transpose(1, 2)
-    att = torch.softmax(qf @ kf.transpose(-1, -2) * (scale if scale is not None else 0.125), dim=-1)
+    sc = qf @ kf.transpose(-1, -2) * (scale if scale is not None else 0.125)
+    if causal:
+        sc = sc + torch.full((nq, sc.shape[-1]), float("-inf")).triu(1)
+    att = torch.softmax(sc, dim=-1)
     return (att @ vf).transpose(1, 2).reshape(b, nq, c).to(bf16)
 
 
@@ -186,6 +193,10 @@ def diag_gaussian(moments, noise, scale=1.0):
     if noise is None:
         return mean * scale
     return (mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) * scale
+
+
+def embed_tokens(ids, tok, pos):
+    return (tok[ids] + pos[None, : ids.shape[1]]).to(bf16)
 
 
 def sinusoid_embedding(t, dim, max_period=10000.0, sin_first=False):
