@@ -20,7 +20,8 @@ scaling).  Beside it, in the same line:
                       list sharded over the N ranks with the NVLink halo exchange; tiled steps/s, bytes exchanged,
                       speed-up over the same list on rank 0 alone; single-image scaling beside it
   batched             the same step with 2 / 4 latents per network call (per-latent step time)
-  images_per_s        BASELINE config 5 sample: infer_dir-style images sharded i mod N, SR3 x8 + 50 cached steps
+  images_per_s        BASELINE config 5 sample (x8, 128^2 -> 1024^2) and config 3 (x4, 256^2 -> 1024^2): infer_dir-style
+                      images sharded i mod N; SR3, VAE encode, 50 cached stage-2 steps, VAE decode, colour fix, uint8
 """
 from __future__ import annotations
 
@@ -293,7 +294,7 @@ def tiled_block(wrapper, dev, rank: int, world: int, pool: int, steps: int, tile
 # ------------------------------------------------------------------------------------------------
 # BASELINE config 5 sample: infer_dir-style images sharded i mod N
 # ------------------------------------------------------------------------------------------------
-def images_block(wrapper, dev, rank: int, world: int, per_rank: int):
+def images_block(wrapper, dev, rank: int, world: int, per_rank: int, upscale: int = 8):
     import torch.distributed as dist
     from b200sr import colorfix, sr3, vae
     from b200sr.driver import RestorationPipeline, run_sharded
@@ -306,10 +307,11 @@ def images_block(wrapper, dev, rank: int, world: int, per_rank: int):
     ae = vae.AutoencoderKLInferenceWrapper(configs.VAE_EMBED_DIM, dict(configs.VAE_DDCONFIG)).add_denoise_encoder().eval()
     weights.fill_(ae.state_dict(), 0)
     pipe = RestorationPipeline(wrapper, diff, first_stage=vae.FirstStage(ae.to(dev)), device=dev,
-                               color_fix=colorfix.wavelet_reconstruction)
+                               color_fix=colorfix.wavelet_reconstruction, upscale=upscale)
+    lr = 1024 // upscale
     n = per_rank * world
     g = torch.Generator().manual_seed(555)
-    images = [torch.rand(1, 3, 128, 128, generator=g) * 2 - 1 for _ in range(n)]
+    images = [torch.rand(1, 3, lr, lr, generator=g) * 2 - 1 for _ in range(n)]
     caps = [tuple({"crossattn": torch.randn(1, 77, 2048, generator=g), "vector": torch.randn(1, 2816, generator=g)}
                   for _ in range(2)) for _ in range(n)]
     run_sharded(pipe, images[:world], caps[:world], rank, world)       # warm-up: one image per rank (graph capture)
@@ -325,7 +327,7 @@ def images_block(wrapper, dev, rank: int, world: int, per_rank: int):
     k = max(1, len(r["indices"]))
     pipe.engine.close()
     return {"images": n, "images_per_rank": per_rank, "seconds": sec, "images_per_s": n / sec,
-            "what": "128^2 -> 1024^2: bicubic x8, SR3 stage 1 (50 ancestral steps at 1024^2), VAE encode, 50 stage-2 steps "
+            "what": f"{lr}^2 -> 1024^2: bicubic x{upscale}, SR3 stage 1 (50 ancestral steps at 1024^2), VAE encode, 50 stage-2 steps "
                     "with the first-block cache (img_threshold 0.3), VAE decode, wavelet colour fix, uint8 pack; image i "
                     "on rank i mod N",
             "first_stage": pipe.first_stage.name if hasattr(pipe.first_stage, "name") else type(pipe.first_stage).__name__,
@@ -434,7 +436,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if not args.no_tiled:
         tiled = tiled_block(wrapper, dev, rank, world, args.tiled_pool, args.tiled_steps, args.tile_batch)
     if not args.no_images:
-        images = images_block(wrapper, dev, rank, world, args.images_per_rank)
+        images = {"x8": images_block(wrapper, dev, rank, world, args.images_per_rank, 8),
+                  "x4": images_block(wrapper, dev, rank, world, 1, 4)}
     if rank != 0:
         return
 

@@ -63,14 +63,16 @@ class FeatureWiseAffine(nn.Module, Packed):
 
 
 def _conv_any(holder: Packed, name: str, conv: nn.Conv2d, x_nhwc, **kw):
-    """3x3 conv for any Cin: Cin % 64 == 0 directly, tiny Cin zero-padded to one 64-channel K chunk."""
+    """3x3 conv for any Cin: Cin % 64 == 0 directly, otherwise zero-padded up to the next multiple of 64 (the 6-channel
+    stem; the 96 / 160-channel concatenations of an inner_channel = 32 network)."""
     cin = conv.weight.shape[1]
     b = holder._pk(name + ".b", (conv.bias,), _F32) if conv.bias is not None else None
     if cin % 64 == 0:
         w = holder._pk(name + ".w", (conv.weight,), ops.pack_conv3x3)
         return ops.conv3x3(x_nhwc, w, b, **kw)
-    w = holder._pk(name + ".w64", (conv.weight,), lambda t: ops.pack_conv3x3_padded(t, 64))
-    return ops.conv3x3(ops.pad_channels(x_nhwc, 64), w, b, **kw)
+    cpad = (cin + 63) // 64 * 64
+    w = holder._pk(name + ".wpad", (conv.weight,), lambda t: ops.pack_conv3x3_padded(t, cpad))
+    return ops.conv3x3(ops.pad_channels(x_nhwc, cpad), w, b, **kw)
 
 
 class Upsample(nn.Module, Packed):
@@ -339,6 +341,7 @@ class GaussianDiffusion(nn.Module):
         return ops.sr3_update(x, eps, noise if t > 0 else None, self._step_table[t])
 
     use_graphs = True  # one CUDA graph per (shape): ~150 launches of a step replayed in one go
+    max_cached_shapes = 4  # least-recently-used input shapes beyond this are dropped (infer_dir runs see many sizes)
 
     @torch.no_grad()
     def _p_sample_graphed(self, x, t, condition_x=None, noise=None):
@@ -347,17 +350,23 @@ class GaussianDiffusion(nn.Module):
         which equals the reference's `noise = zeros` branch (diffusion.py:174)."""
         key = (tuple(x.shape), None if condition_x is None else tuple(condition_x.shape))
         table = self.__dict__.setdefault("_graph_state", {})
-        st = table.get(key)
+        st = table.pop(key, None)
+        if st is not None:
+            table[key] = st                      # most recently used last
         if st is None:
+            while len(table) >= self.max_cached_shapes:   # each entry pins a CUDA graph and its private memory pool
+                table.pop(next(iter(table)))
             st = table[key] = {"x": torch.empty_like(x), "noise": torch.zeros_like(x),
                                "cond": None if condition_x is None else torch.empty_like(condition_x),
                                "level": torch.empty(x.shape[0], 1, dtype=torch.float32, device=x.device),
                                "scal": torch.empty(self._step_table.shape[1], dtype=torch.float32, device=x.device),
                                "graph": None, "cond_src": None}
         st["x"].copy_(x)
-        if condition_x is not None and st["cond_src"] is not condition_x:
-            st["cond"].copy_(condition_x)
-            st["cond_src"] = condition_x
+        src = None if condition_x is None else (condition_x, condition_x._version)
+        if condition_x is not None and (st["cond_src"] is None or st["cond_src"][0] is not condition_x
+                                        or st["cond_src"][1] != condition_x._version):
+            st["cond"].copy_(condition_x)   # also when the same tensor object was refilled in place
+            st["cond_src"] = src
         if t > 0:
             st["noise"].copy_(noise) if noise is not None else st["noise"].normal_()
         else:

@@ -36,3 +36,19 @@ e1.record(); torch.cuda.synchronize()
 res["ms_per_step_graphed"] = e0.elapsed_time(e1) / 5
 print(json.dumps(res))
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"sr3_{S}.json"), "w"))
+# per-launch breakdown of one eager step (CUDA events around every instrumented op, GPU kept busy while the host enqueues)
+from b200sr import ops
+recs = []
+torch.cuda.synchronize(); torch.cuda._sleep(int(0.3 * 1.9e9))
+ops.set_profile(recs)
+with torch.no_grad():
+    net(inp, level)
+ops.set_profile(None); torch.cuda.synchronize()
+agg = {}
+for kind, work, a, b, desc in recs:
+    d = agg.setdefault((kind, desc), [0.0, 0.0, 0]); d[0] += work; d[1] += a.elapsed_time(b); d[2] += 1
+tot = sum(v[1] for v in agg.values())
+print(f"event-timed total {tot:.2f} ms over {sum(v[2] for v in agg.values())} launches")
+for (kind, desc), v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+    rate = v[0] / (v[1] * 1e-3) / 1e12 if v[1] else 0
+    print(f"  {kind:11s} {desc:38s} n={v[2]:3d} {v[1]:7.3f} ms  {rate:8.1f} {'TB/s' if kind in ('group_norm','layer_norm') else 'TF/s'}")
