@@ -133,6 +133,10 @@ int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int
 /* Layout conversion at the nn.Module boundary. */
 int b200sr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, float scale, void* stream);
 int b200sr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, void* stream);
+/* same, from a source with Cs >= C channels per pixel (the first C are converted): the result of a convolution to <= 4
+ * channels that ran on the tensor cores with its output padded to 8 (UNet `out` openaimodel.py:941-947 + wrappers.py:110
+ * `.float()`; SR3 final_conv; the first stage's decoder conv_out). */
+int b200sr_nhwc_bf16_to_nchw_f32_strided(const void* x, float* y, int32_t N, int32_t C, int32_t Cs, int32_t HW, void* stream);
 
 /* Nearest x2 upsample, NHWC bf16 (openaimodel.py:125-145; sr3 unet.py:59-66). */
 int b200sr_upsample2x_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);

@@ -86,6 +86,7 @@ SIGNATURES = {
     "b200sr_softmax_rows": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
     "b200sr_nchw_f32_to_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
     "b200sr_nhwc_bf16_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "b200sr_nhwc_bf16_to_nchw_f32_strided": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "b200sr_upsample2x_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "b200sr_concat_add": (c_int, [P, c_int, P, c_int, P, P, c_i64, P]),
     "b200sr_axpy_bf16": (c_int, [P, P, P, c_float, c_i64, P]),

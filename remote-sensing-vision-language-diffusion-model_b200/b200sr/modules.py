@@ -653,9 +653,8 @@ class UNetModel(nn.Module, Packed):
         """self.out: GN32 + SiLU + 3x3 conv to the latent channels, written as fp32 NCHW (openaimodel.py:941-947)."""
         h = _gn(self.out[0], h_nhwc, silu=True)
         conv = self.out[2]
-        w = self._pk("out.w", (conv.weight,), ops.pack_conv3x3)
-        b = self._pk("out.b", (conv.bias,), _F32)
-        return ops.conv3x3_small(h, w, b, out_nchw_f32=True)
+        w8, b8 = self._pk("out.wb8", (conv.weight, conv.bias), ops.pack_conv3x3_few_out)
+        return ops.conv3x3_to_nchw_f32(h, w8, b8, conv.weight.shape[0])
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """openaimodel.py:973-1007 (plain UNet, skip connections by concatenation)."""

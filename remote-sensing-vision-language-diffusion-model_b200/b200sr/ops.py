@@ -441,6 +441,29 @@ def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def pack_conv3x3_few_out(weight: torch.Tensor, bias: Optional[torch.Tensor]):
+    """[Cout <= 4, Cin, 3, 3] (+ bias) -> packed bf16 [8, 9*Cin] / fp32 [8]: output channels zero-padded to 8 so the
+    convolution runs on the tcgen05 path (the direct warp-per-pixel kernel is 10-50x slower at 128^2 .. 1024^2)."""
+    co = weight.shape[0]
+    w = torch.zeros(8, *weight.shape[1:], dtype=weight.dtype, device=weight.device)
+    w[:co] = weight.detach()
+    b = torch.zeros(8, dtype=torch.float32, device=weight.device)
+    if bias is not None:
+        b[:co] = bias.detach().float()
+    return pack_conv3x3(w), b
+
+
+def conv3x3_to_nchw_f32(x: torch.Tensor, w8: torch.Tensor, b8: torch.Tensor, cout: int) -> torch.Tensor:
+    """3x3 conv (pad 1) to `cout` <= 4 channels, returned as fp32 NCHW: tensor-core conv with the output padded to 8
+    channels (bf16, the reference's autocast output dtype), then the first `cout` channels converted."""
+    y8 = conv3x3(x, w8, b8)
+    n, h, wd, cs = y8.shape
+    out = torch.empty(n, cout, h, wd, dtype=torch.float32, device=x.device)
+    check(_lib.load().b200sr_nhwc_bf16_to_nchw_f32_strided(y8.data_ptr(), out.data_ptr(), n, cout, cs, h * wd, _stream()),
+          "nhwc_to_nchw_strided")
+    return out
+
+
 def upsample2x(x: torch.Tensor) -> torch.Tensor:
     _req(x, bf16, "upsample2x.x")
     n, h, w, c = x.shape

@@ -276,9 +276,8 @@ class UNet(nn.Module, Packed):
         # final_conv: GN + Swish + conv to <= 4 channels, written straight to fp32 NCHW
         blk = self.final_conv.block
         g = _gn(blk[0], h, silu=True)
-        w = self._pk("final.w", (blk[3].weight,), ops.pack_conv3x3)
-        b = self._pk("final.b", (blk[3].bias,), _F32)
-        return ops.conv3x3_small(g, w, b, out_nchw_f32=True)
+        w8, b8 = self._pk("final.wb8", (blk[3].weight, blk[3].bias), ops.pack_conv3x3_few_out)
+        return ops.conv3x3_to_nchw_f32(g, w8, b8, blk[3].weight.shape[0])
 
 
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2):

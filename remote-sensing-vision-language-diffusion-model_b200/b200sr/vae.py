@@ -267,9 +267,8 @@ class Decoder(nn.Module, Packed):
             if i_level != 0:
                 h = self.up[i_level].upsample.forward_nhwc(h)
         h = _gn(self.norm_out, h, silu=True)
-        w = self._pk("conv_out.w", (self.conv_out.weight,), ops.pack_conv3x3)
-        b = self._pk("conv_out.b", (self.conv_out.bias,), _F32)
-        return ops.conv3x3_small(h, w, b, out_nchw_f32=True)
+        w8, b8 = self._pk("conv_out.wb8", (self.conv_out.weight, self.conv_out.bias), ops.pack_conv3x3_few_out)
+        return ops.conv3x3_to_nchw_f32(h, w8, b8, self.conv_out.weight.shape[0])
 
     def forward(self, z, **kwargs):
         ops.require_cuda(z, "b200sr.vae.Decoder")

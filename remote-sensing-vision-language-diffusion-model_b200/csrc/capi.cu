@@ -99,7 +99,7 @@ int embed_tokens(const long long* ids, const float* tok, const float* pos, void*
                  cudaStream_t stream);
 size_t attention_d64_workspace_bytes(int B, int H, int Nq, int Nk);
 int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int HW, float scale, cudaStream_t stream);
-int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStream_t stream);
+int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int Cs, int HW, cudaStream_t stream);
 int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream);
 int concat_add(const void* a, int Ca, const void* b, int Cb, const void* c, void* out, long long rows,
                cudaStream_t stream);
@@ -235,7 +235,11 @@ int b200sr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, 
 }
 int b200sr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, void* stream) {
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;
-  return nhwc_bf16_to_nchw_f32(x, y, N, C, HW, S(stream));
+  return nhwc_bf16_to_nchw_f32(x, y, N, C, C, HW, S(stream));
+}
+int b200sr_nhwc_bf16_to_nchw_f32_strided(const void* x, float* y, int32_t N, int32_t C, int32_t Cs, int32_t HW, void* stream) {
+  if (x == nullptr || y == nullptr) return B200SR_EINVAL;
+  return nhwc_bf16_to_nchw_f32(x, y, N, C, Cs, HW, S(stream));
 }
 int b200sr_upsample2x_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;

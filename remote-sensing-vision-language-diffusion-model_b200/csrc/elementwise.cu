@@ -41,17 +41,20 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
   }
 }
 
-__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int HW) {
+// Cs = channels per pixel in the source (>= C: the first C of them are converted; convolutions to <= 4 channels run
+// with their output padded to 8 channels on the tensor cores)
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int Cs,
+                                             int HW) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-  const __nv_bfloat16* src = x + static_cast<size_t>(n) * C * HW;
+  const __nv_bfloat16* src = x + static_cast<size_t>(n) * Cs * HW;
   float* dst = y + static_cast<size_t>(n) * C * HW;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int pix = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && pix < HW) ? __bfloat162float(src[static_cast<size_t>(pix) * C + c]) : 0.f;
+    tile[i][threadIdx.x] = (c < C && pix < HW) ? __bfloat162float(src[static_cast<size_t>(pix) * Cs + c]) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -66,10 +69,10 @@ int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int HW, float s
   launch_k(nchw_f32_to_nhwc_bf16_kernel, dim3(grid), dim3(block), 0, stream, 1, x, reinterpret_cast<__nv_bfloat16*>(y), C, HW, scale);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
-int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int HW, cudaStream_t stream) {
-  if (N <= 0 || C <= 0 || HW <= 0) return B200SR_EINVAL;
+int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int Cs, int HW, cudaStream_t stream) {
+  if (N <= 0 || C <= 0 || HW <= 0 || Cs < C) return B200SR_EINVAL;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  launch_k(nhwc_bf16_to_nchw_f32_kernel, dim3(grid), dim3(block), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x), y, C, HW);
+  launch_k(nhwc_bf16_to_nchw_f32_kernel, dim3(grid), dim3(block), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x), y, C, Cs, HW);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

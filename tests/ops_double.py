@@ -159,6 +159,10 @@ def cast_bf16(x):
     return x.to(bf16).contiguous()
 
 
+def conv3x3_to_nchw_f32(x, w8, b8, cout):
+    return conv3x3(x, w8, b8).float().permute(0, 3, 1, 2)[:, :cout].contiguous()
+
+
 def upsample2x(x):
     return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
 

@@ -11,9 +11,9 @@ def val(r):
     return v * scale
 ids = collections.defaultdict(dict)
 for r in csv.DictReader(lines[hi:]):
-    if "b200sr" not in r["Kernel Name"]:
+    k = re.sub(r"^(void )?(b200sr::)?", "", r["Kernel Name"].split("(")[0])
+    if k.startswith("at::") or "elementwise_kernel" in k:   # ATen kernels are not part of the step
         continue
-    k = re.sub(r"^(void )?b200sr::", "", r["Kernel Name"].split("(")[0])
     ids[(r["ID"], k)][r["Metric Name"]] = val(r)
 for (i, k), m in ids.items():
     a = fam.setdefault(k, [0, 0.0, 0.0])
