@@ -66,6 +66,16 @@ typedef struct b200sr_epilogue {
                                   kernel's programmatic dependency on its predecessor resolves */
   int32_t w_rows_per_group;    /* 0 = one weight for all rows; otherwise a multiple of 256 */
   int64_t w_group_stride;      /* in weight rows */
+  /* b200sr_conv3x3_bf16, stride 1, W % 8 == 0, H >= 16 only: GroupNorm(+SiLU) of the INPUT fused into the convolution
+   * (ResBlock in_layers / out_layers openaimodel.py:254-258, :289-300; first-stage ResnetBlock model.py:127-141; SR3 Block
+   * unet.py:81-92): x is the raw tensor, a_gn_stats = (mean, rstd) per (image, group) from b200sr_group_norm_stats; every
+   * staged input tile is rewritten as silu(x * rstd * w + (b - mean * rstd * w)) in shared memory before the MMAs read it
+   * (zero padding stays zero), so the normalised tensor never travels through HBM.  NULL = off.                       */
+  const float* a_gn_stats;     /* [N, groups, 2] fp32 */
+  const float* a_gn_weight;    /* [Cin] */
+  const float* a_gn_bias;      /* [Cin] */
+  int32_t a_gn_groups;
+  int32_t a_gn_silu;
 } b200sr_epilogue;
 
 /* D = A[M,K] * W[N,K]^T with fused epilogue; bf16 operands, fp32 accumulate (tcgen05 / TMEM).
@@ -104,6 +114,11 @@ size_t b200sr_group_norm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32
 int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int32_t N, int32_t HW,
                            int32_t C, int32_t groups, float eps, int32_t silu, const void* sft_gamma,
                            const void* sft_beta, const void* raw, float control_scale, void* workspace, void* stream);
+
+/* The statistics pass of b200sr_group_norm_nhwc alone: stats_out[n, g] = (mean, 1/sqrt(var + eps)), fp32 [N, groups, 2],
+ * for a convolution that applies the normalisation itself (b200sr_epilogue.a_gn_*).  Same workspace contract.      */
+int b200sr_group_norm_stats(const void* x, int32_t N, int32_t HW, int32_t C, int32_t groups, float eps, float* stats_out,
+                            void* workspace, void* stream);
 
 /* LayerNorm over the last dim of a bf16 [M, C] matrix (attention.py:437-439). */
 int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* bias, int32_t M, int32_t C, float eps,

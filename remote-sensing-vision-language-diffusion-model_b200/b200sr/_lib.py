@@ -38,6 +38,11 @@ class Epilogue(C.Structure):
         ("w_dynamic", c_int),
         ("w_rows_per_group", c_int),
         ("w_group_stride", c_i64),
+        ("a_gn_stats", c_void_p),
+        ("a_gn_weight", c_void_p),
+        ("a_gn_bias", c_void_p),
+        ("a_gn_groups", c_int),
+        ("a_gn_silu", c_int),
     ]
 
 
@@ -77,6 +82,7 @@ SIGNATURES = {
         c_int,
         [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, c_float, P, P],
     ),
+    "b200sr_group_norm_stats": (c_int, [P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "b200sr_layer_norm": (c_int, [P, P, P, P, c_int, c_int, c_float, P]),
     "b200sr_attention_d64": (
         c_int,

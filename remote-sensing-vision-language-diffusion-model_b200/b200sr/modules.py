@@ -172,6 +172,20 @@ def _conv3x3(holder: Packed, name: str, conv: nn.Conv2d, x_nhwc: torch.Tensor, *
     return ops.conv3x3(x_nhwc, w, b, **kw)
 
 
+FUSE_GN_INTO_CONV = True   # GroupNorm + SiLU applied to the convolution's staged input tiles instead of a pass through HBM
+
+
+def _gn_silu_conv3x3(holder: Packed, name: str, norm: nn.GroupNorm, conv: nn.Conv2d, x_nhwc: torch.Tensor, **kw) -> torch.Tensor:
+    """conv3x3(SiLU(GroupNorm(x))) (openaimodel.py:254-258, :289-300; model.py:127-141; sr3 unet.py:81-92).  Where the
+    halo-path convolution applies (stride 1, W % 8 == 0, H >= 16) only the statistics pass runs as a kernel of its own:
+    the convolution normalises its input tiles in shared memory.  Same arithmetic, same bf16 rounding point, so the
+    result equals the two-kernel form bit for bit."""
+    if FUSE_GN_INTO_CONV and ops.conv3x3_gn_fusable(x_nhwc) and norm.affine:
+        stats = ops.group_norm_stats(x_nhwc, norm.num_groups, norm.eps)
+        return _conv3x3(holder, name, conv, x_nhwc, gn=(stats, norm.weight, norm.bias, norm.num_groups, True), **kw)
+    return _conv3x3(holder, name, conv, _gn(norm, x_nhwc, silu=True), **kw)
+
+
 def _linear(holder: Packed, name: str, lin, x: torch.Tensor, **kw) -> torch.Tensor:
     w = holder._pk(name + ".w", (lin.weight,), ops.pack_linear)
     b = holder._pk(name + ".b", (lin.bias,), _F32) if lin.bias is not None else None
@@ -250,11 +264,9 @@ class ResBlock(TimestepBlock, Packed):
         emb_out = pre.get(id(self)) if pre is not None else None
         if emb_out is None:  # stand-alone use of the block
             emb_out = _linear(self, "emb", self.emb_layers[1], _silu_of(emb), out_fp32=True)
-        h = _gn(self.in_layers[0], x, silu=True)
-        h = _conv3x3(self, "conv1", self.in_layers[2], h, rowvec=emb_out)
-        h = _gn(self.out_layers[0], h, silu=True)
+        h = _gn_silu_conv3x3(self, "conv1", self.in_layers[0], self.in_layers[2], x, rowvec=emb_out)
         skip = x if isinstance(self.skip_connection, nn.Identity) else _linear(self, "skip", self.skip_connection, x)
-        return _conv3x3(self, "conv2", self.out_layers[3], h, residual=skip)
+        return _gn_silu_conv3x3(self, "conv2", self.out_layers[0], self.out_layers[3], h, residual=skip)
 
     def forward(self, x, emb):
         return from_nhwc(self.forward_nhwc(to_nhwc(x), emb))

@@ -256,9 +256,12 @@ def conv3x3(
     out: Optional[torch.Tensor] = None,
     force_bn: int = 0,
     pad_lo: int = 1,
+    gn=None,
 ) -> torch.Tensor:
     """3x3 conv, pad 1.  x: [N, H, W, Cin] bf16; w: packed [Cout, 9*Cin]; rowvec: fp32 [N, Cout]
-    (added per image: ResBlock emb); residual: bf16 [N, OH, OW, Cout].  pad_lo = 0 (stride 2): pad (0, 1, 0, 1)."""
+    (added per image: ResBlock emb); residual: bf16 [N, OH, OW, Cout].  pad_lo = 0 (stride 2): pad (0, 1, 0, 1).
+    gn = (stats, weight, bias, groups, silu): x is the RAW tensor and GroupNorm(+SiLU) is applied to the staged input
+    tiles inside the kernel (stats from group_norm_stats; only where conv3x3_gn_fusable(x, stride))."""
     _req(x, bf16, "conv3x3.x")
     _req(w, bf16, "conv3x3.w")
     n, h, wd, cin = x.shape
@@ -270,6 +273,11 @@ def conv3x3(
     ldc = out.stride(2)
     ldr = residual.stride(2) if residual is not None else 0
     e = _epilogue(out, ldc, bias, rowvec, 0, residual, ldr, False, False, alpha, act)
+    if gn is not None:
+        stats, gw, gb, groups, gsilu = gn
+        _req(stats, torch.float32, "conv3x3.gn.stats")
+        e.a_gn_stats, e.a_gn_weight, e.a_gn_bias = stats.data_ptr(), gw.data_ptr(), gb.data_ptr()
+        e.a_gn_groups, e.a_gn_silu = int(groups), int(gsilu)
     with _Timed("conv3x3", 2.0 * n * oh * ow * cout * 9 * cin, f"{n}x{h}x{wd} Cin{cin} Cout{cout} s{stride}"):
         rc = _lib.load().b200sr_conv3x3_bf16(
             x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, pad_lo, C.byref(e), force_bn, _stream()
@@ -333,6 +341,25 @@ def group_norm(
         )
     check(rc, f"group_norm N={n} HW={hw} C={c}", kernels=2)
     return y
+
+
+def conv3x3_gn_fusable(x: torch.Tensor, stride: int = 1) -> bool:
+    """Shapes the halo-path convolution (and with it the fused input GroupNorm) covers."""
+    return stride == 1 and x.dim() == 4 and x.shape[2] % 8 == 0 and x.shape[1] >= 16 and x.shape[3] % 64 == 0
+
+
+def group_norm_stats(x: torch.Tensor, groups: int = 32, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per (image, group) of channels-last x: fp32 [N, groups, 2] (the statistics pass of group_norm)."""
+    _req(x, bf16, "group_norm_stats.x")
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    lib = _lib.load()
+    ws = _workspace(x.device, lib.b200sr_group_norm_workspace_bytes(n, hw, c, groups))
+    stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
+    with _Timed("group_norm", 2.0 * x.numel(), f"N{n} HW{hw} C{c} stats"):
+        rc = lib.b200sr_group_norm_stats(x.data_ptr(), n, hw, c, groups, eps, stats.data_ptr(), ws.data_ptr(), _stream())
+    check(rc, f"group_norm_stats N={n} HW={hw} C={c}")
+    return stats
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

@@ -114,6 +114,10 @@ class Block(nn.Module, Packed):
                                    nn.Conv2d(dim, dim_out, 3, padding=1))
 
     def forward_nhwc(self, x, **kw):
+        from .modules import _gn_silu_conv3x3
+
+        if x.shape[-1] % 64 == 0:   # GroupNorm + Swish folded into the convolution's input tiles where it applies
+            return _gn_silu_conv3x3(self, "conv", self.block[0], self.block[3], x, **kw)
         return _conv_any(self, "conv", self.block[3], _gn(self.block[0], x, silu=True), **kw)
 
     def forward(self, x):

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import Packed, _F32, _conv3x3, _gn, _linear, from_nhwc, to_nhwc
+from .modules import Packed, _F32, _conv3x3, _gn, _gn_silu_conv3x3, _linear, from_nhwc, to_nhwc
 
 bf16 = torch.bfloat16
 
@@ -99,10 +99,9 @@ class ResnetBlock(nn.Module, Packed):
 
     def forward_nhwc(self, x, temb=None):
         assert temb is None
-        h = _conv3x3(self, "conv1", self.conv1, _gn(self.norm1, x, silu=True))
-        h = _gn(self.norm2, h, silu=True)
+        h = _gn_silu_conv3x3(self, "conv1", self.norm1, self.conv1, x)
         skip = x if self.in_channels == self.out_channels else _linear(self, "nin", self.nin_shortcut, x)
-        return _conv3x3(self, "conv2", self.conv2, h, residual=skip)   # x + h in the epilogue
+        return _gn_silu_conv3x3(self, "conv2", self.norm2, self.conv2, h, residual=skip)   # x + h in the epilogue
 
     def forward(self, x, temb=None):
         return from_nhwc(self.forward_nhwc(to_nhwc(x), temb))
@@ -204,7 +203,7 @@ class Encoder(nn.Module, Packed):
         h = self.mid.block_1.forward_nhwc(h)
         h = self.mid.attn_1.forward_nhwc(h) if not isinstance(self.mid.attn_1, nn.Identity) else h
         h = self.mid.block_2.forward_nhwc(h)
-        return _conv3x3(self, "conv_out", self.conv_out, _gn(self.norm_out, h, silu=True))   # [B, h, w, 2 z] bf16
+        return _gn_silu_conv3x3(self, "conv_out", self.norm_out, self.conv_out, h)   # [B, h, w, 2 z] bf16
 
     def forward(self, x):
         ops.require_cuda(x, "b200sr.vae.Encoder")

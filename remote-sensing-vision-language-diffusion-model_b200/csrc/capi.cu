@@ -89,6 +89,8 @@ size_t group_norm_workspace_bytes(int N, int HW, int C, int groups);
 int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int N, int HW, int C, int groups,
                     float eps, int silu, const void* sft_gamma, const void* sft_beta, const void* raw,
                     float control_scale, float* workspace, cudaStream_t stream);
+int group_norm_stats(const void* x, int N, int HW, int C, int groups, float eps, float* stats_out, float* workspace,
+                     cudaStream_t stream);
 int layer_norm(const void* x, void* y, const float* weight, const float* bias, int M, int C, float eps,
                cudaStream_t stream);
 int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream);
@@ -150,6 +152,11 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.w_dynamic = e->w_dynamic;
   a.w_rows_per_group = e->w_rows_per_group;
   a.w_group_stride = e->w_group_stride;
+  a.a_gn_stats = e->a_gn_stats;
+  a.a_gn_weight = e->a_gn_weight;
+  a.a_gn_bias = e->a_gn_bias;
+  a.a_gn_groups = e->a_gn_groups;
+  a.a_gn_silu = e->a_gn_silu;
   return a;
 }
 
@@ -203,6 +210,11 @@ int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const fl
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;
   return group_norm_nhwc(x, y, weight, bias, N, HW, C, groups, eps, silu, sft_gamma, sft_beta, raw, control_scale,
                          reinterpret_cast<float*>(workspace), S(stream));
+}
+int b200sr_group_norm_stats(const void* x, int32_t N, int32_t HW, int32_t C, int32_t groups, float eps, float* stats_out,
+                            void* workspace, void* stream) {
+  if (x == nullptr) return B200SR_EINVAL;
+  return group_norm_stats(x, N, HW, C, groups, eps, stats_out, reinterpret_cast<float*>(workspace), S(stream));
 }
 int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* bias, int32_t M, int32_t C, float eps,
                       void* stream) {

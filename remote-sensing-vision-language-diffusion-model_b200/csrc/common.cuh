@@ -373,6 +373,10 @@ struct EpilogueArgs {
   int w_dynamic;            // != 0: the W operand is produced by an earlier kernel (no prefetch ahead of griddepcontrol.wait)
   int w_rows_per_group;     // > 0: rows [g * w_rows_per_group, ...) of A use weight rows offset by g * w_group_stride
   long long w_group_stride;
+  const float* a_gn_stats;  // conv3x3 (halo path) only: GroupNorm(+SiLU) of the input fused into the A tile
+  const float* a_gn_weight;
+  const float* a_gn_bias;
+  int a_gn_groups, a_gn_silu;
 };
 
 }  // namespace b200sr

@@ -62,7 +62,8 @@ static constexpr int A_HALO_BYTES = 23 * 1024;                         // stage 
 static constexpr int MAX_A_HALO_STAGES = 4;
 static constexpr int MAX_B_STAGES = 16;
 static constexpr int BAR_REGION_BYTES = 512;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 192;        // producer, MMA issuer, 4 epilogue warps
+static constexpr int GEMM_THREADS_XFORM = 256;  // + 2 warps that normalise the halo tile in place (fused GroupNorm)
 static constexpr int TMEM_COLS = 512;
 static constexpr int ACC_STAGE_COLS = 256;
 
@@ -103,6 +104,12 @@ struct GemmParams {
   int w_dynamic;
   int w_rows_per_group;
   long long w_group_stride;
+  // mode 3, fused GroupNorm(+SiLU) of the INPUT: y = silu(x * a[n, c] + b[n, c]) applied to the halo tile in shared memory
+  // between TMA arrival and the MMAs (a = rstd * gamma, b = beta - mean * a); padding pixels stay zero
+  const float* gn_stats;   // [NB][groups] (mean, rstd), nullptr = off
+  const float* gn_weight;  // [Cin]
+  const float* gn_bias;    // [Cin]
+  int gn_groups, gn_silu;
 };
 
 static constexpr int SOFTMAX_SEG = 80;  // columns per head segment in the softmax epilogue (77 text tokens, padded)
@@ -178,7 +185,7 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 
 template <int kCluster>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS_XFORM, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -219,10 +226,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + MAX_B_STAGES;                          // [16]
   uint64_t* a_full = empty_bar + MAX_B_STAGES;                            // [4]  mode 3
   uint64_t* a_empty = a_full + MAX_A_HALO_STAGES;                         // [4]  mode 3
-  uint64_t* tmem_full = a_empty + MAX_A_HALO_STAGES;
+  uint64_t* a_land = a_empty + MAX_A_HALO_STAGES;                         // [4]  mode 3 + fused GN: this CTA's tile landed
+  uint64_t* tmem_full = a_land + MAX_A_HALO_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_epi = reinterpret_cast<float*>(smem + ring_bytes + BAR_REGION_BYTES);  // [4 warps][256] staged bias
+  float* s_ab = s_epi + 4 * 256;                                                  // fused GN: [a_stages][64 a | 64 b]
+  const bool xform = halo && p.gn_stats != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -233,8 +243,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (halo) {
       for (int s = 0; s < p.a_stages; ++s) {
-        mbar_init(&a_full[s], 1);
+        // plain: TMA bytes of both CTAs land on the leader's barrier; fused GN: one arrive per CTA once its tile is
+        // normalised (the TMA completes on the CTA-local a_land instead)
+        mbar_init(&a_full[s], xform ? kCluster : 1);
         mbar_init(&a_empty[s], 1);
+        mbar_init(&a_land[s], 1);
       }
     }
     for (int s = 0; s < 2; ++s) {
@@ -308,7 +321,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cc = 0; cc < p.kc_per_tap; ++cc) {
           mbar_wait(&a_empty[sa], pa ^ 1);
           uint8_t* dst = smem + sa * A_HALO_BYTES;
-          if (kCluster == 1) {
+          if (xform) {
+            mbar_expect_tx(&a_land[sa], static_cast<uint32_t>(A_HALO_TX_BYTES));
+            tma_load_4d(dst, &tmA, &a_land[sa], cc * BLOCK_K, tw * HALO_TILE_W - 1, th * HALO_TILE_H - 1, tn);
+          } else if (kCluster == 1) {
             mbar_expect_tx(&a_full[sa], a_tx);
             tma_load_4d(dst, &tmA, &a_full[sa], cc * BLOCK_K, tw * HALO_TILE_W - 1, th * HALO_TILE_H - 1, tn);
           } else {
@@ -566,6 +582,80 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ================================ fused GroupNorm(+SiLU) of the halo tile (2 warps) ================================
+    // Mirrors the producer's tile order.  Per 64-channel chunk: thread t computes (a, b) of channel cc*64 + t from the
+    // statistics of its group, the 64 threads wait for this CTA's tile (TMA, 128B swizzle: pixel row p holds its eight
+    // 16-byte channel groups at chunk index j ^ (p & 7)), rewrite every in-image pixel in place and hand the tile to
+    // the MMA issuer (of the pair's leader).  Pixels outside the image were zero-filled by the TMA and stay zero: the
+    // convolution pads the NORMALISED tensor.
+    if (xform) {
+      const int t = threadIdx.x - 6 * 32;   // 0..63
+      const int cpg = p.Cin / p.gn_groups;
+      int sa = 0;
+      uint32_t pa = 0;
+      pdl_wait();   // statistics come from the preceding kernel
+      for (int work = work0; work < num_work; work += work_stride) {
+        const int m_blk = (work % m_groups) * kCluster + static_cast<int>(rank);
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int tn = m_blk / (p.tiles_w * p.tiles_h);
+        const bool img_ok = tn < p.NB;
+        for (int cc = 0; cc < p.kc_per_tap; ++cc) {
+          float* ab = s_ab + sa * 128;
+          if (img_ok) {
+            const int c = cc * BLOCK_K + t;
+            const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + tn * p.gn_groups + c / cpg);
+            const float a = st.y * __ldg(p.gn_weight + c);
+            ab[t] = a;
+            ab[64 + t] = __ldg(p.gn_bias + c) - st.x * a;
+          }
+          mbar_wait(&a_land[sa], pa);
+          asm volatile("bar.sync 2, 64;" ::: "memory");   // (a, b) visible to both warps
+          uint8_t* tile = smem + sa * A_HALO_BYTES;
+          if (img_ok) {
+            for (int idx = t; idx < HALO_W * HALO_H * 8; idx += 64) {
+              const int pix = idx >> 3, jc = idx & 7;
+              const int hy = pix / HALO_W, hx = pix - hy * HALO_W;
+              const int iy = th * HALO_TILE_H - 1 + hy, ix = tw * HALO_TILE_W - 1 + hx;
+              if (iy < 0 || iy >= p.OH || ix < 0 || ix >= p.OW) continue;
+              const int j = jc ^ (pix & 7);   // logical 8-channel group stored at physical chunk jc of this row
+              uint4* q = reinterpret_cast<uint4*>(tile + pix * 128 + jc * 16);
+              const uint4 u = *q;
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+              const float4 a0 = *reinterpret_cast<const float4*>(ab + j * 8), a1 = *reinterpret_cast<const float4*>(ab + j * 8 + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(ab + 64 + j * 8), b1 = *reinterpret_cast<const float4*>(ab + 64 + j * 8 + 4);
+              const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w4[e]);
+                v[2 * e] = f.x * sc[2 * e] + sh[2 * e];
+                v[2 * e + 1] = f.y * sc[2 * e + 1] + sh[2 * e + 1];
+              }
+              if (p.gn_silu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+              }
+              *q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+          asm volatile("bar.sync 2, 64;" ::: "memory");
+          if (t == 0) {
+            if (kCluster == 1)
+              mbar_arrive(&a_full[sa]);
+            else
+              mbar_arrive_cluster(mapa_cluster(smem_u32(&a_full[sa]), 0));
+          }
+          if (++sa == p.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
         }
       }
     }
@@ -863,7 +953,8 @@ static long long* g_gemm_trace = nullptr;
 
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/;
+  const int xform_bytes = p.gn_stats != nullptr ? MAX_A_HALO_STAGES * 128 * 4 : 0;   // (a, b) of one chunk per halo stage
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/ - xform_bytes;
   const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
   const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
   size_t ring_bytes;
@@ -885,7 +976,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
     p.a_stages = 0;
     ring_bytes = static_cast<size_t>(stages) * stage_bytes;
   }
-  const size_t smem_bytes = ring_bytes + 1024 + BAR_REGION_BYTES + 4096;
+  const size_t smem_bytes = ring_bytes + 1024 + BAR_REGION_BYTES + 4096 + xform_bytes;
 #ifdef B200SR_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
@@ -898,7 +989,8 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
   const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
   const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
-  const cudaError_t err = launch_k(gemm_conv_kernel<kCluster>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream,
+  const cudaError_t err = launch_k(gemm_conv_kernel<kCluster>, dim3(grid),
+                                   dim3(p.gn_stats != nullptr ? GEMM_THREADS_XFORM : GEMM_THREADS), smem_bytes, stream,
                                    kCluster, tmA, tmB, p);
   return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
@@ -921,6 +1013,17 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.w_dynamic = e.w_dynamic;
   p.w_rows_per_group = e.w_rows_per_group;
   p.w_group_stride = e.w_group_stride;
+  p.gn_stats = e.a_gn_stats;
+  p.gn_weight = e.a_gn_weight;
+  p.gn_bias = e.a_gn_bias;
+  p.gn_groups = e.a_gn_groups;
+  p.gn_silu = e.a_gn_silu;
+  if (e.a_gn_stats != nullptr) {
+    // fused input GroupNorm: halo convolution only, affine parameters required
+    if (p.mode != 3 || e.a_gn_weight == nullptr || e.a_gn_bias == nullptr || e.a_gn_groups <= 0 ||
+        (p.Cin % e.a_gn_groups) != 0)
+      return B200SR_EINVAL;
+  }
   if (e.softmax_valid < 0 || e.softmax_valid > SOFTMAX_SEG) return B200SR_EINVAL;
   if (e.softmax_valid > 0 && (e.geglu || e.out_fp32 || e.residual != nullptr || e.rowvec != nullptr || e.bias != nullptr ||
                               e.act != 0 || (p.N % SOFTMAX_SEG) != 0))

@@ -30,8 +30,8 @@ __device__ __forceinline__ float2 gn_mean_rstd(double sum, double sumsq, double 
 // pixels t / C8, t / C8 + P, ... of its chunk, so consecutive threads read consecutive 16 B.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ workspace, int HW, int C, int groups,
-                int pix_per_cta, int chunks, int N, float eps) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ workspace, float2* __restrict__ stats_out,
+                int HW, int C, int groups, int pix_per_cta, int chunks, int N, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_red[];  // [P][C] sums, then [P][C] sums of squares (no atomics: deterministic)
@@ -47,7 +47,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ workspa
   float* s_sq = s_red + P * C;
   // workspace: [N] arrival counters (zero between launches) | [N][groups] (mean, rstd) | partial sums
   unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
-  float2* stats = reinterpret_cast<float2*>(workspace + GN_WS_COUNTER_FLOATS);
+  float2* stats = stats_out != nullptr ? stats_out : reinterpret_cast<float2*>(workspace + GN_WS_COUNTER_FLOATS);
   float* partial = workspace + GN_WS_COUNTER_FLOATS + 2 * static_cast<size_t>(N) * groups;
 
   float s[8], q[8];
@@ -332,7 +332,7 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
   dim3 grid(chunks, N);
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * static_cast<size_t>(P) * C * sizeof(float), stream, 1, reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                    workspace, HW, C, groups, ppc, chunks, N, eps);
+                                                                    workspace, static_cast<float2*>(nullptr), HW, C, groups, ppc, chunks, N, eps);
   GnApplyArgs a;
   a.x = reinterpret_cast<const __nv_bfloat16*>(x);
   a.stats = workspace + GN_WS_COUNTER_FLOATS;
@@ -349,6 +349,21 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   a.pix_per_cta = ppc;
   a.silu = silu;
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 2 * groups * sizeof(float), stream, 1, a);
+  return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+}
+
+// Statistics pass alone: (mean, rstd) per (image, group) into `stats_out` [N][groups][2] for a consumer that applies
+// the normalisation itself (the halo convolution's fused input GroupNorm, gemm_conv.cu).
+int group_norm_stats(const void* x, int N, int HW, int C, int groups, float eps, float* stats_out, float* workspace,
+                     cudaStream_t stream) {
+  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || (C % 8) != 0 || (C % groups) != 0 || C / 8 > 1024)
+    return B200SR_EINVAL;
+  if (workspace == nullptr || stats_out == nullptr || N > GN_WS_COUNTER_FLOATS) return B200SR_EINVAL;
+  int threads, P, ppc, chunks;
+  gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
+  launch_k(gn_stats_kernel, dim3(chunks, N), dim3(threads), 2 * static_cast<size_t>(P) * C * sizeof(float), stream, 1,
+           reinterpret_cast<const __nv_bfloat16*>(x), workspace, reinterpret_cast<float2*>(stats_out), HW, C, groups, ppc,
+           chunks, N, eps);
   return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

@@ -60,7 +60,28 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu
     return y
 
 
-def conv3x3(x, w, bias=None, *, stride=1, rowvec=None, residual=None, alpha=1.0, act=0, out=None, force_bn=0, pad_lo=1):
+def conv3x3_gn_fusable(x, stride=1):
+    return stride == 1 and x.dim() == 4 and x.shape[2] % 8 == 0 and x.shape[1] >= 16 and x.shape[3] % 64 == 0
+
+
+def group_norm_stats(x, groups=32, eps=1e-5):
+    n, c = x.shape[0], x.shape[-1]
+    xf = x.float().reshape(n, -1, groups, c // groups)
+    mean = xf.mean(dim=(1, 3))
+    var = xf.var(dim=(1, 3), unbiased=False)
+    return torch.stack([mean, torch.rsqrt(var + eps)], dim=-1)
+
+
+def conv3x3(x, w, bias=None, *, stride=1, rowvec=None, residual=None, alpha=1.0, act=0, out=None, force_bn=0, pad_lo=1,
+            gn=None):
+    if gn is not None:
+        stats, gw, gb, groups, gsilu = gn
+        c = x.shape[-1]
+        mean = stats[..., 0].repeat_interleave(c // groups, dim=1)[:, None, None, :]
+        rstd = stats[..., 1].repeat_interleave(c // groups, dim=1)[:, None, None, :]
+        a = rstd * gw
+        y = x.float() * a + (gb - mean * a)
+        x = (F.silu(y) if gsilu else y).to(bf16)
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     w4 = w.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)

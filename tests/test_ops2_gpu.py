@@ -64,3 +64,42 @@ def test_copy_batch_and_strips():
         ops.strip_add(ops.tile_weighted_strip(tile, w, y0, x0, sh, sw), acc2, 8 + y0, 24 + x0)
     assert torch.equal(acc1, acc2)
     assert torch.equal(acc1[:, :, 8:40, 24:56], tile * w)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,extras", [
+    (2, 32, 32, 1280, 1280, "rowvec"), (2, 128, 128, 320, 320, "residual"), (1, 64, 64, 640, 320, ""),
+    (1, 16, 8, 64, 64, ""), (1, 256, 256, 64, 64, "residual"), (3, 48, 40, 128, 256, "rowvec"), (1, 1024, 64, 128, 64, ""),
+])
+def test_conv3x3_with_fused_input_groupnorm(n, h, w, cin, cout, extras):
+    """GroupNorm + SiLU applied to the staged input tiles inside the halo convolution == GroupNorm kernel followed by the
+    convolution, bit for bit (same arithmetic, same bf16 rounding point), and == a torch fp32 reference within bf16."""
+    import torch.nn.functional as F
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + h + cin)
+    x = (torch.randn(n, h, w, cin, generator=g, device="cuda") * 1.5 + 0.3).to(bf16)
+    wt = torch.randn(cout, cin, 3, 3, generator=g, device="cuda") * (1.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g, device="cuda") * 0.1
+    gw = 1 + 0.1 * torch.randn(cin, generator=g, device="cuda")
+    gb = 0.1 * torch.randn(cin, generator=g, device="cuda")
+    kw = {}
+    if extras == "rowvec":
+        kw["rowvec"] = torch.randn(n, cout, generator=g, device="cuda")
+    if extras == "residual":
+        kw["residual"] = torch.randn(n, h, w, cout, generator=g, device="cuda").to(bf16)
+    assert ops.conv3x3_gn_fusable(x)
+    wp = ops.pack_conv3x3(wt)
+    two = ops.conv3x3(ops.group_norm(x, gw, gb, groups=32, eps=1e-5, silu=True), wp, b, **kw)
+    stats = ops.group_norm_stats(x, 32, 1e-5)
+    fused = ops.conv3x3(x, wp, b, gn=(stats, gw, gb, 32, True), **kw)
+    assert torch.equal(fused, two)
+    xf = x.float().permute(0, 3, 1, 2)
+    y = F.silu(F.group_norm(xf, 32, gw, gb, 1e-5)).to(bf16).float()
+    ref = F.conv2d(y, wt.to(bf16).float(), b, padding=1).permute(0, 2, 3, 1)
+    if "rowvec" in kw:
+        ref = ref + kw["rowvec"][:, None, None, :]
+    if "residual" in kw:
+        ref = ref + kw["residual"].float()
+    assert rel_l2(fused, ref) < 5e-3
+    mean = xf.reshape(n, 32, -1).mean(-1)
+    assert torch.allclose(stats[..., 0], mean, atol=2e-3)
