@@ -177,10 +177,11 @@ FUSE_GN_INTO_CONV = True   # GroupNorm + SiLU applied to the convolution's stage
 
 def _gn_silu_conv3x3(holder: Packed, name: str, norm: nn.GroupNorm, conv: nn.Conv2d, x_nhwc: torch.Tensor, **kw) -> torch.Tensor:
     """conv3x3(SiLU(GroupNorm(x))) (openaimodel.py:254-258, :289-300; model.py:127-141; sr3 unet.py:81-92).  Where the
-    halo-path convolution applies (stride 1, W % 8 == 0, H >= 16) only the statistics pass runs as a kernel of its own:
-    the convolution normalises its input tiles in shared memory.  Same arithmetic, same bf16 rounding point, so the
-    result equals the two-kernel form bit for bit."""
-    if FUSE_GN_INTO_CONV and ops.conv3x3_gn_fusable(x_nhwc) and norm.affine:
+    halo-path convolution applies (stride 1, W % 8 == 0, H >= 16) and the output fits one N tile (<= 256 channels: the
+    high-resolution levels of SR3 and of the first stage) only the statistics pass runs as a kernel of its own: the
+    convolution normalises its input tiles in shared memory.  Same arithmetic, same bf16 rounding point, so the result
+    equals the two-kernel form bit for bit."""
+    if FUSE_GN_INTO_CONV and ops.conv3x3_gn_fusable(x_nhwc, 1, conv.out_channels) and norm.affine:
         stats = ops.group_norm_stats(x_nhwc, norm.num_groups, norm.eps)
         return _conv3x3(holder, name, conv, x_nhwc, gn=(stats, norm.weight, norm.bias, norm.num_groups, True), **kw)
     return _conv3x3(holder, name, conv, _gn(norm, x_nhwc, silu=True), **kw)

@@ -63,7 +63,8 @@ static constexpr int MAX_A_HALO_STAGES = 4;
 static constexpr int MAX_B_STAGES = 16;
 static constexpr int BAR_REGION_BYTES = 512;
 static constexpr int GEMM_THREADS = 192;        // producer, MMA issuer, 4 epilogue warps
-static constexpr int GEMM_THREADS_XFORM = 256;  // + 2 warps that normalise the halo tile in place (fused GroupNorm)
+static constexpr int XFORM_WARPS = 6;   // 12 warps in all: the register file is allocated in 4-warp granules
+static constexpr int GEMM_THREADS_XFORM = GEMM_THREADS + 32 * XFORM_WARPS;  // + warps that normalise the halo tile in place (fused GroupNorm)
 static constexpr int TMEM_COLS = 512;
 static constexpr int ACC_STAGE_COLS = 256;
 
@@ -184,8 +185,10 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int kCluster>
-__global__ void __launch_bounds__(GEMM_THREADS_XFORM, 1)
+// kXform: the instantiation with the extra GroupNorm warps (320 threads, <= 204 registers); the plain one keeps 192
+// threads and the full register budget its epilogues want.
+template <int kCluster, bool kXform>
+__global__ void __launch_bounds__(kXform ? GEMM_THREADS_XFORM : GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -231,8 +234,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_epi = reinterpret_cast<float*>(smem + ring_bytes + BAR_REGION_BYTES);  // [4 warps][256] staged bias
-  float* s_ab = s_epi + 4 * 256;                                                  // fused GN: [a_stages][64 a | 64 b]
-  const bool xform = halo && p.gn_stats != nullptr;
+  float* s_ab = s_epi + 4 * 256;                                                  // fused GN: [Cin] a | [Cin] b of one image
+  const bool xform = kXform && halo && p.gn_stats != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -245,7 +248,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int s = 0; s < p.a_stages; ++s) {
         // plain: TMA bytes of both CTAs land on the leader's barrier; fused GN: one arrive per CTA once its tile is
         // normalised (the TMA completes on the CTA-local a_land instead)
-        mbar_init(&a_full[s], xform ? kCluster : 1);
+        mbar_init(&a_full[s], xform ? kCluster * XFORM_WARPS : 1);   // one arrive per transform warp of every CTA
         mbar_init(&a_empty[s], 1);
         mbar_init(&a_land[s], 1);
       }
@@ -405,7 +408,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 0) {
+  } else if (!kXform && warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
@@ -497,7 +500,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (!kXform && warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0 && leader) {
       const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M * kCluster, static_cast<uint32_t>(p.BN), 0, 0);
@@ -593,9 +596,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the MMA issuer (of the pair's leader).  Pixels outside the image were zero-filled by the TMA and stay zero: the
     // convolution pads the NORMALISED tensor.
     if (xform) {
-      const int t = threadIdx.x - 6 * 32;   // 0..63
+      constexpr int XT = 32 * XFORM_WARPS;
+      const int t = threadIdx.x - 6 * 32;   // 0 .. XT-1
+      const int xw = t >> 5;                 // transform warp 0 .. XFORM_WARPS-1: owns pixels xw, xw + XFORM_WARPS, ... of every tile
       const int cpg = p.Cin / p.gn_groups;
-      int sa = 0;
+      float* ab = s_ab;                      // [Cin] a | [Cin] b of the image this CTA is working on
+      int sa = 0, cur_n = -1;
       uint32_t pa = 0;
       pdl_wait();   // statistics come from the preceding kernel
       for (int work = work0; work < num_work; work += work_stride) {
@@ -604,32 +610,41 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int th = (m_blk / p.tiles_w) % p.tiles_h;
         const int tn = m_blk / (p.tiles_w * p.tiles_h);
         const bool img_ok = tn < p.NB;
-        for (int cc = 0; cc < p.kc_per_tap; ++cc) {
-          float* ab = s_ab + sa * 128;
-          if (img_ok) {
-            const int c = cc * BLOCK_K + t;
+        if (img_ok && tn != cur_n) {
+          // per-channel scale / shift of this image, once per image (not per chunk: the loads would sit on every
+          // chunk's path to the tensor core)
+          asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");   // previous image's table no longer read
+          for (int c = t; c < p.Cin; c += XT) {
             const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + tn * p.gn_groups + c / cpg);
             const float a = st.y * __ldg(p.gn_weight + c);
-            ab[t] = a;
-            ab[64 + t] = __ldg(p.gn_bias + c) - st.x * a;
+            ab[c] = a;
+            ab[p.Cin + c] = __ldg(p.gn_bias + c) - st.x * a;
           }
+          asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+          cur_n = tn;
+        }
+        for (int cc = 0; cc < p.kc_per_tap; ++cc) {
           mbar_wait(&a_land[sa], pa);
-          asm volatile("bar.sync 2, 64;" ::: "memory");   // (a, b) visible to both warps
           uint8_t* tile = smem + sa * A_HALO_BYTES;
           if (img_ok) {
-            for (int idx = t; idx < HALO_W * HALO_H * 8; idx += 64) {
-              const int pix = idx >> 3, jc = idx & 7;
+            // lane = (pixel within a group of 4, LOGICAL 8-channel group j): the lane's 8 scales / shifts live in registers
+            // for the whole chunk (reading them per element would cost 4x the tile's own shared-memory traffic, which
+            // the tensor core's operand reads have no room for); a quarter-warp still covers one whole 128-byte pixel
+            // row per access, its chunks permuted by the swizzle (physical chunk = j ^ (row & 7)).
+            const int j = lane & 7;
+            const float* ac = ab + cc * BLOCK_K + j * 8;
+            const float* bc = ab + p.Cin + cc * BLOCK_K + j * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(ac), a1 = *reinterpret_cast<const float4*>(ac + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bc), b1 = *reinterpret_cast<const float4*>(bc + 4);
+            const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            for (int pix = xw * 4 + (lane >> 3); pix < HALO_W * HALO_H; pix += 4 * XFORM_WARPS) {
               const int hy = pix / HALO_W, hx = pix - hy * HALO_W;
               const int iy = th * HALO_TILE_H - 1 + hy, ix = tw * HALO_TILE_W - 1 + hx;
               if (iy < 0 || iy >= p.OH || ix < 0 || ix >= p.OW) continue;
-              const int j = jc ^ (pix & 7);   // logical 8-channel group stored at physical chunk jc of this row
-              uint4* q = reinterpret_cast<uint4*>(tile + pix * 128 + jc * 16);
+              uint4* q = reinterpret_cast<uint4*>(tile + pix * 128 + ((j ^ (pix & 7)) << 4));
               const uint4 u = *q;
               const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-              const float4 a0 = *reinterpret_cast<const float4*>(ab + j * 8), a1 = *reinterpret_cast<const float4*>(ab + j * 8 + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(ab + 64 + j * 8), b1 = *reinterpret_cast<const float4*>(ab + 64 + j * 8 + 4);
-              const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-              const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float v[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -644,9 +659,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             }
           }
-          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-          asm volatile("bar.sync 2, 64;" ::: "memory");
-          if (t == 0) {
+          // each warp hands over its own pixel rows: fence its generic-proxy writes for the tensor core's (async proxy)
+          // reads, then one arrive per warp — no CTA-wide barrier on the tile's way to the MMAs
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
             if (kCluster == 1)
               mbar_arrive(&a_full[sa]);
             else
@@ -712,7 +729,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (threadIdx.x == 64) GT(9);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STAGE_COLS;
-      if (p.softmax_valid > 0) {
+      if (!kXform && p.softmax_valid > 0) {
         // Row softmax over each SOFTMAX_SEG-column head segment of the accumulator (logits already in log2
         // units), written as bf16 probabilities; columns >= softmax_valid of a segment are padding -> 0.
         for (int sg = 0; sg * SOFTMAX_SEG < p.BN; ++sg) {
@@ -761,8 +778,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       uint32_t a_cur[32], a_nxt[32];
-      if (p.softmax_valid <= 0) tmem_ld32(t_row, a_cur);
-      for (int c = 0; c < (p.softmax_valid > 0 ? 0 : p.BN); c += 32) {
+      if (kXform || p.softmax_valid <= 0) tmem_ld32(t_row, a_cur);
+      for (int c = 0; c < ((!kXform && p.softmax_valid > 0) ? 0 : p.BN); c += 32) {
         tmem_ld_wait();
         const bool more = c + 32 < p.BN;
         if (more) {
@@ -786,7 +803,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
             v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
           }
-          if (p.geglu) {
+          if (!kXform && p.geglu) {
             // columns [0,16) = value, [16,32) = gate of the same 16 output features
             const long long ocol = col0 >> 1;
             float o[16];
@@ -846,7 +863,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = quick_gelu_f(v[j]);
             }
-            if (p.out_fp32) {
+            if (!kXform && p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -953,7 +970,7 @@ static long long* g_gemm_trace = nullptr;
 
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int xform_bytes = p.gn_stats != nullptr ? MAX_A_HALO_STAGES * 128 * 4 : 0;   // (a, b) of one chunk per halo stage
+  const int xform_bytes = p.gn_stats != nullptr ? ((p.Cin * 8 + 1023) / 1024) * 1024 : 0;   // per-channel (a, b) of one image
   const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/ - xform_bytes;
   const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
   const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
@@ -961,6 +978,10 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
   if (p.mode == 3) {
     const int b_stage_bytes = HALO_TAPS * b_sub_bytes;
     p.a_stages = p.kc_per_tap >= 2 ? 2 : 1;
+    // fused input GroupNorm: TMA latency + the in-place transform sit between a tile's landing and its MMAs, so a third
+    // halo stage pays — unless it squeezes the weight ring below three stages (BN = 256: a kernel row of weights is
+    // 48 KB; two rows in flight no longer cover the TMA latency, measured +15 us per 1280-channel convolution)
+    if (p.gn_stats != nullptr && (smem_budget - 3 * A_HALO_BYTES) / b_stage_bytes >= 3) p.a_stages = 3;
     int stages = (smem_budget - p.a_stages * A_HALO_BYTES) / b_stage_bytes;
     if (stages > MAX_B_STAGES) stages = MAX_B_STAGES;
     if (stages < 2) return B200SR_EINVAL;
@@ -982,16 +1003,21 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
 #endif
   static bool attr_set[64] = {false};  // per device (and per kCluster instantiation)
   if (first_use_on_device(attr_set)) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(gemm_conv_kernel<kCluster, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess)
       return B200SR_ELAUNCH;
   }
   const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
   const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
-  const cudaError_t err = launch_k(gemm_conv_kernel<kCluster>, dim3(grid),
-                                   dim3(p.gn_stats != nullptr ? GEMM_THREADS_XFORM : GEMM_THREADS), smem_bytes, stream,
-                                   kCluster, tmA, tmB, p);
+  const cudaError_t err =
+      p.gn_stats != nullptr
+          ? launch_k(gemm_conv_kernel<kCluster, true>, dim3(grid), dim3(GEMM_THREADS_XFORM), smem_bytes, stream, kCluster, tmA,
+                     tmB, p)
+          : launch_k(gemm_conv_kernel<kCluster, false>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, kCluster, tmA, tmB,
+                     p);
   return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 

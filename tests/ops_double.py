@@ -60,8 +60,9 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu
     return y
 
 
-def conv3x3_gn_fusable(x, stride=1):
-    return stride == 1 and x.dim() == 4 and x.shape[2] % 8 == 0 and x.shape[1] >= 16 and x.shape[3] % 64 == 0
+def conv3x3_gn_fusable(x, stride=1, cout=None):
+    ok = stride == 1 and x.dim() == 4 and x.shape[2] % 8 == 0 and x.shape[1] >= 16 and x.shape[3] % 64 == 0
+    return ok and (cout is None or cout <= 256)
 
 
 def group_norm_stats(x, groups=32, eps=1e-5):

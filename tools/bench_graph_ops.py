@@ -95,6 +95,23 @@ if which in ("all", "attn"):
 if which in ("all", "norm"):
     ln_case(2048, 1280, 270); ln_case(8192, 640, 42)
     gn_case(2, 1024, 1280, 28); gn_case(2, 16384, 320, 12); gn_case(2, 4096, 640, 17)
+if which == "gnconv":
+    for (N, H, W, Cin, Cout) in ((2, 32, 32, 1280, 1280), (2, 64, 64, 640, 640), (2, 128, 128, 320, 320), (2, 32, 32, 2560, 1280),
+                                 (1, 1024, 1024, 64, 64), (1, 512, 512, 128, 128)):
+        nw = max(2, min(REP, int(160e6 / (Cout * 9 * Cin * 2)) + 1))
+        ws = [r(Cout, 9 * Cin, scale=0.02) for _ in range(nw)]
+        x = r(N, H, W, Cin); b = torch.randn(Cout, device=dev)
+        gw = torch.ones(Cin, device=dev); gb = torch.zeros(Cin, device=dev)
+        fl = 2.0 * N * H * W * Cout * 9 * Cin
+        t0 = graph_time(lambda i: ops.conv3x3(x, ws[i % nw], b))
+        t1 = graph_time(lambda i: ops.conv3x3(ops.group_norm(x, gw, gb, silu=True), ws[i % nw], b))
+        t2 = graph_time(lambda i: ops.conv3x3(x, ws[i % nw], b, gn=(ops.group_norm_stats(x), gw, gb, 32, True)))
+        st = ops.group_norm_stats(x)
+        t3 = graph_time(lambda i: ops.conv3x3(x, ws[i % nw], b, gn=(st, gw, gb, 32, True)))
+        t4 = graph_time(lambda i: ops.conv3x3(x, ws[i % nw], b, gn=(st, gw, gb, 32, False)))
+        t5 = graph_time(lambda i: ops.group_norm_stats(x))
+        print(f"conv {N}x{H}x{W} {Cin}->{Cout}: plain conv {t0:6.1f} us | GN(2 kernels)+conv {t1:6.1f} | stats+fused conv {t2:6.1f} | "
+              f"fused conv alone {t3:6.1f} (no SiLU {t4:6.1f}) | stats kernel {t5:5.1f}")
 tot = 0.0
 print(f"{'op':46s} {'us/launch':>9s} {'TF/s|TB/s':>9s} {'n/step':>6s} {'ms/step':>8s}")
 for name, t, rate, n in rows:
