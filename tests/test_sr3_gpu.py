@@ -51,11 +51,11 @@ def test_unet_and_loop_match_reference_golden(net):
     assert torch.equal(sr, sr_eager)
 
 
-@pytest.mark.parametrize("size", [128, 512])
+@pytest.mark.parametrize("size", [128, 512, 1024])
 def test_unet_vs_oracle(net, size):
-    """BASELINE config 1 size (x8, 16^2 -> 128^2) and a 512^2 image (mid-block attention over 1024 tokens of width
-    512, computed as GEMMs + row softmax; the 1024^2 case of config 3 is tools/sr3_1024.py): one UNet call vs the
-    fp32 oracle on the GPU."""
+    """BASELINE config 1 size (x8, 16^2 -> 128^2), a 512^2 image, and config 3's stage-1 size 1024^2 (three
+    single-head attentions over 16384 tokens of width 512: score GEMM, single-pass row softmax, P V GEMM; GroupNorm folded
+    into the 64 / 128 / 256-channel convolutions): one UNet call vs the fp32 oracle on the GPU."""
     from oracle import inputs, sr3 as osr3
 
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -70,3 +70,31 @@ def test_unet_vs_oracle(net, size):
     err = rel_l2(out, ref)
     print(f"sr3 {size}^2 eps rel-L2 vs fp32 oracle: {err:.4e}")
     assert err < 1e-2
+
+
+def test_unet_2048_bounded_memory(net):
+    """BASELINE config 4's stage-1 size: 2048^2 puts 65536 tokens into the single-head attention; the T x T score matrix
+    (17 GB in fp32) is never allocated: the scores of at most ops.SCORE_CHUNK_BYTES (1 GB) worth of query rows exist at a
+    time.  No oracle at this size (its attention would need the 17 GB): finiteness, peak memory and consistency between
+    two chunk sizes."""
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.rand(1, 6, 2048, 2048, generator=g, device="cuda") * 2 - 1
+    level = torch.tensor([[0.3]], device="cuda")
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    out = net(x, level)
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    print(f"sr3 2048^2: peak extra memory {peak / 2**30:.1f} GiB")
+    assert out.shape == (1, 3, 2048, 2048) and torch.isfinite(out).all()
+    assert peak < 12 * 2**30
+    old = ops.SCORE_CHUNK_BYTES
+    try:
+        ops.SCORE_CHUNK_BYTES = 256 << 20
+        out2 = net(x, level)
+    finally:
+        ops.SCORE_CHUNK_BYTES = old
+    assert rel_l2(out2, out) < 2e-3   # chunking only changes the GEMM tiling of the score rows
