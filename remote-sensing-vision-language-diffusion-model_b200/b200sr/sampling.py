@@ -127,7 +127,7 @@ class Stage2Engine:
 
     def __init__(self, wrapper, num_steps=50, s_churn=5.0, s_noise=1.003, cfg_scale=4.0, cfg_scale_min=7.5,
                  control_scale=1.0, use_graphs=True, device="cuda", hoist_text_kv=True, dual_stream=True, split_cfg=False,
-                 precompute_emb=True):
+                 precompute_emb=True, lazy_control=True):
         self.wrapper = wrapper
         self.hoist_text_kv = hoist_text_kv
         # drive the two networks directly (and concurrently) when the wrapper is our own ControlWrapper
@@ -136,6 +136,9 @@ class Stage2Engine:
         # run the two CFG halves (independent through the whole network) as two concurrent stream pairs
         self.split_cfg = split_cfg and self.dual_stream
         self.precompute_emb = precompute_emb and self._direct and not self.split_cfg
+        # first-block cache: run the control net only on a miss (its output is unused on a hit; the similarity test reads
+        # the UNet encoder's output only).  Same function, same decisions; a hit costs 4.27 instead of 10.14 TFLOP.
+        self.lazy_control = lazy_control and self._direct
         self._side = None
         self._streams = None
         self.sched = StepSchedule(num_steps, s_churn, 0.0, float("inf"), s_noise, cfg_scale, cfg_scale_min)
@@ -430,33 +433,75 @@ class Stage2Engine:
         st["x_next"], st["den"] = x_next, den
 
     def _body_stage1(self):
+        """First call of the cache protocol (sampling.py:556-571): everything the similarity test needs.  The test reads
+        only `h`, the output of the UNet's last input block — not the control features.  The reference computes the
+        control net here regardless (wrappers.py:91-95) and throws it away on every cache hit; the engine defers it to
+        the second call, which only runs on a miss (`lazy_control`): a hit then costs the UNet encoder alone."""
         st = self._static
         x_hat, net_in = ops.sampler_pre(st["x"], st["noise"], st["sc"], 2)
-        if self._direct:
+        st["x_hat"] = x_hat
+        if self._direct and self.lazy_control:
+            unet = self.wrapper.diffusion_model
+            emb_u, _ = self._embs()
+            emb = emb_u if emb_u is not None else unet._embed(st["t"], self._vector())
+            h, hs = unet._input_stage(net_in, emb, self.cond["crossattn"])
+            st["lazy"] = (net_in, h, hs, emb)
+            st["info"] = None
+        elif self._direct:
             control, h, hs, emb, _ = self._net_first_half(net_in)
-            info = {"mode": "input", "h": h.permute(0, 3, 1, 2), "hs": [t.permute(0, 3, 1, 2) for t in hs], "emb": emb,
-                    "context": self.cond["crossattn"], "control": [t.permute(0, 3, 1, 2) for t in control],
-                    "adapter_idx": len(self.wrapper.diffusion_model.project_modules) - 1, "control_idx": len(control) - 1}
+            st["info"] = {"mode": "input", "h": h.permute(0, 3, 1, 2), "hs": [t.permute(0, 3, 1, 2) for t in hs], "emb": emb,
+                          "context": self.cond["crossattn"], "control": [t.permute(0, 3, 1, 2) for t in control],
+                          "adapter_idx": len(self.wrapper.diffusion_model.project_modules) - 1,
+                          "control_idx": len(control) - 1}
         else:
-            info = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self._wrapper_cond(), self.control_scale,
-                                "input_stage1", None)
-        st["x_hat"], st["info"] = x_hat, info
-        h = info["h"].permute(0, 2, 3, 1)
+            st["info"] = self.wrapper(net_in.permute(0, 3, 1, 2), st["t"], self._wrapper_cond(), self.control_scale,
+                                      "input_stage1", None)
+            h = st["info"]["h"].permute(0, 2, 3, 1)
+        if st["info"] is not None:
+            h = st["info"]["h"].permute(0, 2, 3, 1)
+        st["h"] = h
         if "prev_h" not in st:
             st["prev_h"] = torch.zeros_like(h)
             st["final"] = torch.zeros_like(st["x"])
         st["sim"] = ops.rel_l1_similarity(st["prev_h"], h, st["thr"])
 
     def _body_stage2(self):
+        """Second call (a miss, sampling.py:577-596): context.prev = h.clone(); the rest of the network; the sampler update;
+        context.final_decode = denoised.clone()."""
         st = self._static
-        info = st["info"]
-        # context.prev = h.clone() (sampling.py:580) and, after the update, context.final_decode = denoised.clone()
-        h_src = info["h"].permute(0, 2, 3, 1)
+        h_src = st["h"]
         if h_src.is_contiguous() and h_src.dtype == st["prev_h"].dtype:
             ops.copy_batch([(st["prev_h"], h_src)])
         else:  # a foreign wrapper's partial_info
             st["prev_h"].copy_(h_src)
-        eps = self.wrapper(st["x_hat"], st["t"], self._wrapper_cond(), self.control_scale, "input_stage2", info)
+        if st["info"] is None:
+            # lazy control: the control net and the adapter work that depends only on it run now, on the side stream, while
+            # the main stream runs the middle block; they join before the first adapter
+            net_in, h, hs, emb = st["lazy"]
+            w, c = self.wrapper, self.cond
+            unet = w.diffusion_model
+            _, emb_c = self._embs()
+            lq = ops_to_nhwc(c["control"])
+            if self.dual_stream:
+                main = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side), ops.workspace_slot(1):
+                    control = w.control_model.forward_nhwc(lq, st["t"], net_in, c["crossattn"], self._vector(), emb=emb_c)
+                    pre = unet.precompute_adapters(control)
+                hm = unet._middle(h, emb, c["crossattn"])
+                main.wait_stream(self._side)
+                if not torch.cuda.is_current_stream_capturing():
+                    for t_ in list(control) + [v for d in pre.values() for v in d.values()]:
+                        t_.record_stream(main)
+            else:
+                control = w.control_model.forward_nhwc(lq, st["t"], net_in, c["crossattn"], self._vector(), emb=emb_c)
+                pre = None
+                hm = unet._middle(h, emb, c["crossattn"])
+            eps = unet._output_stage(hm, hs, emb, c["crossattn"], control, self.control_scale, pre=pre, middle_done=True)
+        else:
+            eps = self.wrapper(st["x_hat"], st["t"], self._wrapper_cond(), self.control_scale, "input_stage2", st["info"])
         x_next, den = ops.sampler_post(eps, st["x_hat"], st["sc"], True, True)
         ops.copy_batch([(st["final"], den)])
         st["x_next"] = x_next
