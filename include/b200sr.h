@@ -111,6 +111,9 @@ int b200sr_conv3x3_small(const void* x, const void* w, const float* bias, const 
  * per-image arrival counters: zero it once after allocation; every call leaves it zeroed.
  * Calls that may run concurrently (different streams) need distinct workspaces.                */
 size_t b200sr_group_norm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups);
+/* kernels one b200sr_group_norm_nhwc call of this shape enqueues: 1 (tensors that fit the SMs' shared memory: statistics,
+ * per-image barrier and apply in one kernel) or 2 (statistics kernel + apply kernel); 0 for invalid shapes. */
+int b200sr_group_norm_launches(int32_t N, int32_t HW, int32_t C, int32_t groups);
 int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int32_t N, int32_t HW,
                            int32_t C, int32_t groups, float eps, int32_t silu, const void* sft_gamma,
                            const void* sft_beta, const void* raw, float control_scale, void* workspace, void* stream);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "b200sr_diag_gaussian": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "b200sr_conv3x3_small": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200sr_group_norm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "b200sr_group_norm_launches": (c_int, [c_int, c_int, c_int, c_int]),
     "b200sr_group_norm_nhwc": (
         c_int,
         [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, c_float, P, P],

@@ -339,7 +339,7 @@ def group_norm(
             x.data_ptr(), y.data_ptr(), _ptr(weight), _ptr(bias), n, hw, c, groups, eps, int(silu), _ptr(sft_gamma),
             _ptr(sft_beta), _ptr(raw), float(control_scale), ws.data_ptr(), _stream()
         )
-    check(rc, f"group_norm N={n} HW={hw} C={c}", kernels=2)
+    check(rc, f"group_norm N={n} HW={hw} C={c}", kernels=max(1, lib.b200sr_group_norm_launches(n, hw, c, groups)))
     return y
 
 

@@ -86,6 +86,7 @@ int pointwise_small(const void* x, const float* w, const float* bias, void* y, i
 int diag_gaussian(const float* moments, const float* noise, float* z, int N, int C, int HW, float scale,
                   cudaStream_t stream);
 size_t group_norm_workspace_bytes(int N, int HW, int C, int groups);
+int group_norm_launches(int N, int HW, int C, int groups);
 int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int N, int HW, int C, int groups,
                     float eps, int silu, const void* sft_gamma, const void* sft_beta, const void* raw,
                     float control_scale, float* workspace, cudaStream_t stream);
@@ -203,6 +204,9 @@ int b200sr_conv3x3_small(const void* x, const void* w, const float* bias, const 
 size_t b200sr_group_norm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups) {
   if (N <= 0 || HW <= 0 || C < 8 || groups <= 0) return 0;
   return group_norm_workspace_bytes(N, HW, C, groups);
+}
+int b200sr_group_norm_launches(int32_t N, int32_t HW, int32_t C, int32_t groups) {
+  return group_norm_launches(N, HW, C, groups);
 }
 int b200sr_group_norm_nhwc(const void* x, void* y, const float* weight, const float* bias, int32_t N, int32_t HW,
                            int32_t C, int32_t groups, float eps, int32_t silu, const void* sft_gamma,

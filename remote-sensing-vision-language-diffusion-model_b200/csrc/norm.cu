@@ -10,6 +10,7 @@
 //   nn.LayerNorm(C) eps 1e-5                          sgm/modules/attention.py:437-439
 //   SR3 nn.GroupNorm(32, C) + Swish                   models/sr3_model/sr3_modules/unet.py:81-92
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200sr {
 
@@ -294,6 +295,199 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnApplyArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// GroupNorm in ONE kernel for tensors that fit the SMs' shared memory (<= ~12 MB: every GroupNorm of the 32^2 and most
+// of the 64^2 levels of the stage-2 networks).  Each CTA keeps its pixel chunk in shared memory between the two phases:
+//   phase 1  load the chunk (one 16-byte vector per thread and pixel), per-channel sums, per-(chunk, group) partials
+//   barrier  per-image arrival counter; CTAs spin until all `chunks` CTAs of their image have published
+//   fold     every CTA folds the image's partials itself, in a fixed order (deterministic), fp64
+//   phase 2  normalise / activate / modulate from shared memory, write y
+// x is read from L2 / HBM once, and the statistics -> apply dependency costs a spin on an L2 counter instead of a
+// kernel boundary.  The launcher only takes this path when the whole grid is resident at once (chunks * N <= SMs, one
+// CTA of <= 100 KB per SM, so two such kernels on two streams still fit side by side); the spin traps instead of
+// hanging if that assumption is ever violated.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+gn_fused_kernel(const GnApplyArgs a, float* __restrict__ workspace, int chunks, int N, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const int C = a.C, HW = a.HW, groups = a.groups;
+  const int C8 = C >> 3;
+  const int P = blockDim.x / C8;
+  const int cv = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p_begin = chunk * a.pix_per_cta;
+  const int p_end = min(HW, p_begin + a.pix_per_cta);
+  const int cpg = C / groups;
+  uint4* s_x = reinterpret_cast<uint4*>(s_raw);                                     // [pix_per_cta][C8]
+  float* s_sum = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.pix_per_cta) * C * 2);   // [P][C]
+  float* s_sq = s_sum + P * C;                                                      // [P][C]
+  float* s_ab = s_sq + P * C;                                                       // [groups] mean | [groups] rstd
+  unsigned int* arrive = reinterpret_cast<unsigned int*>(workspace);                // [N]
+  unsigned int* depart = arrive + 128;                                              // [N]
+  float* partial = workspace + GN_WS_COUNTER_FLOATS + 2 * static_cast<size_t>(N) * groups;
+  const size_t img = static_cast<size_t>(n) * HW;
+
+  // ---- phase 1 ----
+  if (pl < P) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const uint4* base = reinterpret_cast<const uint4*>(a.x) + img * C8 + cv;
+    for (int pix = p_begin + pl; pix < p_end; pix += P) {
+      const uint4 u = __ldg(base + static_cast<size_t>(pix) * C8);
+      s_x[(pix - p_begin) * C8 + cv] = u;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s[2 * j] += f.x;
+        q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y;
+        q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_sum[pl * C + cv * 8 + j] = s[j];
+      s_sq[pl * C + cv * 8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float sa = 0.f, sb = 0.f;
+    for (int pp = 0; pp < P; ++pp)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        sa += s_sum[pp * C + c];
+        sb += s_sq[pp * C + c];
+      }
+    float* dst = partial + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
+    dst[0] = sa;
+    dst[1] = sb;
+  }
+  __syncthreads();
+  // ---- per-image barrier ----
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&arrive[n], 1u);
+    long long t0 = 0;
+    unsigned int spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(arrive + n) : "memory");
+      if (v >= static_cast<unsigned int>(chunks)) break;
+      if (++spins == 64u) t0 = clock64();
+      if (spins > 64u) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) __trap();   // the grid was not resident at once: fail loudly, never hang
+      }
+    }
+  }
+  __syncthreads();
+  // ---- fold (same order in every CTA and on every replay) ----
+  {
+    const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * chunks * groups;
+    const int T = blockDim.x;
+    const int R = T / groups > 0 ? T / groups : 1;       // partial rows handled in parallel per group
+    double* s_d = reinterpret_cast<double*>(s_sum);       // the [P][C] buffers are dead; 2 * R * groups doubles fit (R * groups <= T)
+    const int g = threadIdx.x % groups, r0 = threadIdx.x / groups;
+    double da = 0.0, db = 0.0;
+    if (r0 < R)
+      for (int k = r0; k < chunks; k += R) {
+        const float2 v = __ldcg(src + static_cast<size_t>(k) * groups + g);
+        da += v.x;
+        db += v.y;
+      }
+    if (r0 < R) {
+      s_d[r0 * groups + g] = da;
+      s_d[(R + r0) * groups + g] = db;
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      da = 0.0;
+      db = 0.0;
+      for (int r = 0; r < R; ++r) {
+        da += s_d[r * groups + threadIdx.x];
+        db += s_d[(R + r) * groups + threadIdx.x];
+      }
+      const float2 m = gn_mean_rstd(da, db, 1.0 / (static_cast<double>(HW) * cpg), eps);
+      s_ab[threadIdx.x] = m.x;
+      s_ab[groups + threadIdx.x] = m.y;
+    }
+    __syncthreads();
+  }
+  // the last CTA of the image to get here re-arms both counters (every CTA has passed the spin by then)
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&depart[n], 1u);
+    if (prev == static_cast<unsigned int>(chunks) - 1u) {
+      depart[n] = 0u;
+      __threadfence();
+      arrive[n] = 0u;
+    }
+  }
+  if (pl >= P) return;
+  // ---- phase 2: apply from shared memory ----
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float w = a.weight ? a.weight[c] : 1.f;
+    const float b = a.bias ? a.bias[c] : 0.f;
+    sc[j] = s_ab[groups + g] * w;
+    sh[j] = b - s_ab[g] * sc[j];
+  }
+  const bool sft = a.sft_gamma != nullptr;
+  const float cs = a.control_scale;
+  for (int pix = p_begin + pl; pix < p_end; pix += P) {
+    const size_t off = (img + pix) * C8 + cv;
+    const uint4 u = s_x[(pix - p_begin) * C8 + cv];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[2 * j] = f.x * sc[2 * j] + sh[2 * j];
+      v[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+    }
+    if (a.silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
+    if (sft) {
+      const uint4 ug = __ldg(reinterpret_cast<const uint4*>(a.sft_gamma) + off);
+      const uint4 ub = __ldg(reinterpret_cast<const uint4*>(a.sft_beta) + off);
+      const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w};
+      const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g2 = unpack_bf16x2(wg[j]);
+        const float2 b2 = unpack_bf16x2(wb[j]);
+        v[2 * j] = v[2 * j] * (1.f + g2.x) + b2.x;
+        v[2 * j + 1] = v[2 * j + 1] * (1.f + g2.y) + b2.y;
+      }
+      if (a.raw != nullptr && cs != 1.f) {
+        const uint4 ur = __ldg(reinterpret_cast<const uint4*>(a.raw) + off);
+        const uint32_t wr[4] = {ur.x, ur.y, ur.z, ur.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 r2 = unpack_bf16x2(wr[j]);
+          v[2 * j] = v[2 * j] * cs + r2.x * (1.f - cs);
+          v[2 * j + 1] = v[2 * j + 1] * cs + r2.y * (1.f - cs);
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(a.y)[off] = o;
+  }
+}
+
 static void gn_geometry(int N, int HW, int C, int* threads, int* P, int* pix_per_cta, int* chunks) {
   const int C8 = C / 8;
   int p = 256 / C8;
@@ -315,6 +509,28 @@ static void gn_geometry(int N, int HW, int C, int* threads, int* P, int* pix_per
   *chunks = (HW + ppc - 1) / ppc;
 }
 
+static bool gn_fused_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("B200SR_GN_FUSED");
+    return e == nullptr || e[0] != '0';
+  }();
+  return v;
+}
+// one-kernel path: the whole grid resident at once (<= one CTA per SM), the chunk and the reduction scratch within
+// 100 KB of shared memory, the fold's per-group parallelism covered by the thread count
+static bool gn_fused_eligible(int N, int C, int groups, int threads, int P, int ppc, int chunks, size_t* smem_out) {
+  const size_t smem = static_cast<size_t>(ppc) * C * 2 + 2 * static_cast<size_t>(P) * C * sizeof(float) + 2 * groups * sizeof(float);
+  const bool fold_fits = groups <= threads && 2 * static_cast<size_t>(threads) * sizeof(double) <= 2 * static_cast<size_t>(P) * C * sizeof(float);
+  if (smem_out) *smem_out = smem;
+  return gn_fused_enabled() && chunks * N <= num_sms() && N <= 128 && smem <= 100 * 1024 && fold_fits;
+}
+int group_norm_launches(int N, int HW, int C, int groups) {
+  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || (C % 8) != 0 || (C % groups) != 0) return 0;
+  int threads, P, ppc, chunks;
+  gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
+  return gn_fused_eligible(N, C, groups, threads, P, ppc, chunks, nullptr) ? 1 : 2;
+}
+
 size_t group_norm_workspace_bytes(int N, int HW, int C, int groups) {
   int threads, P, ppc, chunks;
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
@@ -331,6 +547,31 @@ int group_norm_nhwc(const void* x, void* y, const float* weight, const float* bi
   int threads, P, ppc, chunks;
   gn_geometry(N, HW, C, &threads, &P, &ppc, &chunks);
   dim3 grid(chunks, N);
+  {
+    size_t smem = 0;
+    if (gn_fused_eligible(N, C, groups, threads, P, ppc, chunks, &smem)) {
+      static bool attr_set[64] = {false};
+      if (first_use_on_device(attr_set))
+        cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      GnApplyArgs a;
+      a.x = reinterpret_cast<const __nv_bfloat16*>(x);
+      a.stats = nullptr;
+      a.weight = weight;
+      a.bias = bias;
+      a.y = reinterpret_cast<__nv_bfloat16*>(y);
+      a.sft_gamma = reinterpret_cast<const __nv_bfloat16*>(sft_gamma);
+      a.sft_beta = reinterpret_cast<const __nv_bfloat16*>(sft_beta);
+      a.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
+      a.control_scale = control_scale;
+      a.HW = HW;
+      a.C = C;
+      a.groups = groups;
+      a.pix_per_cta = ppc;
+      a.silu = silu;
+      launch_k(gn_fused_kernel, dim3(grid), dim3(threads), smem, stream, 1, a, workspace, chunks, N, eps);
+      return cudaGetLastError() == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
+    }
+  }
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * static_cast<size_t>(P) * C * sizeof(float), stream, 1, reinterpret_cast<const __nv_bfloat16*>(x),
                                                                     workspace, static_cast<float2*>(nullptr), HW, C, groups, ppc, chunks, N, eps);
   GnApplyArgs a;
