@@ -76,6 +76,22 @@ typedef struct b200sr_epilogue {
   const float* a_gn_bias;      /* [Cin] */
   int32_t a_gn_groups;
   int32_t a_gn_silu;
+  /* b200sr_gemm_bf16 only: the LayerNorm in front of a Linear (BasicTransformerBlock norm1/2/3 -> to_q/k/v, GEGLU proj,
+   * attention.py:376-486) folded around the GEMM, so the normalised activations never exist in HBM and no LayerNorm
+   * kernel runs.  With W' = W * gamma (rounded to bf16; this is the W passed in), colsum[n] = sum_k W'[n, k] and
+   * shift[n] = sum_k W[n, k] * beta[k] (+ the Linear's bias):
+   *     LN(x) W^T + b  =  rstd[m] * (x W'^T - mean[m] * colsum) + shift
+   * The GEMM runs on the RAW rows x; (mean, rstd) of each row come from ln_parts partial (sum, sum of squares) pairs,
+   * ln_stats[q * M + m], which the GEMM that produced x wrote through ln_stats_out (one pair per N tile of that
+   * GEMM: ln_parts = ceil(N_producer / b200sr_gemm_n_tile(M, N_producer, K_producer)), taken over the bf16 values it
+   * stored).  colsum / shift are [weight groups, N] (one row unless w_rows_per_group > 0).  Works with every epilogue
+   * term, including geglu and the per-head softmax.  NULL = off.                                                  */
+  const float* ln_stats;       /* [ln_parts, M, 2] fp32 */
+  int32_t ln_parts;
+  const float* ln_colsum;
+  const float* ln_shift;
+  float ln_eps;
+  float* ln_stats_out;         /* [n tiles, M, 2] fp32 or NULL; bf16 output, no geglu / softmax */
 } b200sr_epilogue;
 
 /* D = A[M,K] * W[N,K]^T with fused epilogue; bf16 operands, fp32 accumulate (tcgen05 / TMEM).
@@ -85,6 +101,10 @@ typedef struct b200sr_epilogue {
  * lda in elements; K % 8 == 0; N % 8 == 0; force_bn = 0 lets the library pick the N tile.    */
 int b200sr_gemm_bf16(const void* A, int64_t lda, const void* W, int32_t M, int32_t N, int32_t K,
                      const b200sr_epilogue* epi, int32_t force_bn, void* stream);
+
+/* The N tile b200sr_gemm_bf16 uses for an [M, K] x [N, K]^T product with force_bn = 0 and no softmax epilogue
+ * (the number of ln_stats_out partials per row is ceil(N / tile)).  0 on invalid sizes.                          */
+int b200sr_gemm_n_tile(int32_t M, int32_t N, int32_t K);
 
 /* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16, weights [Cout, 3, 3, Cin] bf16, as an
  * implicit GEMM on the same tcgen05 mainloop (each tap = one shifted TMA box, zero fill = pad).

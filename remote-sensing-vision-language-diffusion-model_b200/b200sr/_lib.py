@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SR_LIB selects another in-tree build of the same ABI (A/B kernel experiments); default = the product library
 LIB_PATH = os.path.join(_HERE, os.environ.get("B200SR_LIB", "libb200sr.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_i64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -43,6 +43,12 @@ class Epilogue(C.Structure):
         ("a_gn_bias", c_void_p),
         ("a_gn_groups", c_int),
         ("a_gn_silu", c_int),
+        ("ln_stats", c_void_p),
+        ("ln_parts", c_int),
+        ("ln_colsum", c_void_p),
+        ("ln_shift", c_void_p),
+        ("ln_eps", c_float),
+        ("ln_stats_out", c_void_p),
     ]
 
 
@@ -73,6 +79,7 @@ SIGNATURES = {
     "b200sr_abi_version": (c_int, []),
     "b200sr_num_sms": (c_int, []),
     "b200sr_gemm_bf16": (c_int, [P, c_i64, P, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
+    "b200sr_gemm_n_tile": (c_int, [c_int, c_int, c_int]),
     "b200sr_conv3x3_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
     "b200sr_pointwise_small": (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_int, c_float, P]),
     "b200sr_diag_gaussian": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),

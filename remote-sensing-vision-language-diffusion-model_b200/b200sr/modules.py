@@ -23,6 +23,7 @@ accumulation, fp32 normalisation statistics and softmax; activations are stored 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -172,6 +173,9 @@ def _conv3x3(holder: Packed, name: str, conv: nn.Conv2d, x_nhwc: torch.Tensor, *
     return ops.conv3x3(x_nhwc, w, b, **kw)
 
 
+# LayerNorm folded around the GEMM behind it (transformer blocks): statistics ride from each residual GEMM's epilogue to the
+# next GEMM's epilogue, no LayerNorm kernel and no normalised copy of the residual stream (ops.gemm `ln` / `want_stats`)
+FUSE_LN_INTO_GEMM = os.environ.get("B200SR_FUSE_LN", "1") != "0"
 FUSE_GN_INTO_CONV = True   # GroupNorm + SiLU applied to the convolution's staged input tiles instead of a pass through HBM
 
 
@@ -283,7 +287,13 @@ class GEGLU(nn.Module, Packed):
         super().__init__()
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
-    def forward(self, x):
+    def forward(self, x, ln=None):
+        """`ln` = (LayerNorm module, RowStats of x): x is the raw residual stream and the norm is folded into the GEMM."""
+        if ln is not None:
+            norm, stats = ln
+            w, colsum, shift = self._pk("proj_ln", (self.proj.weight, self.proj.bias, norm.weight, norm.bias),
+                                        ops.pack_geglu_ln)
+            return ops.gemm(tokens_bf16(x), w, None, geglu=True, ln=(stats, colsum, shift, norm.eps))
         w, b = self._pk("proj", (self.proj.weight, self.proj.bias), ops.pack_geglu)
         return ops.gemm(tokens_bf16(x), w, b, geglu=True)
 
@@ -298,8 +308,8 @@ class FeedForward(nn.Module, Packed):
         dim_out = dim_out or dim
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
-    def forward(self, x, residual: Optional[torch.Tensor] = None):
-        return _linear(self, "out", self.net[2], self.net[0](x), residual=residual)
+    def forward(self, x, residual: Optional[torch.Tensor] = None, ln=None, want_stats: bool = False):
+        return _linear(self, "out", self.net[2], self.net[0](x, ln=ln), residual=residual, want_stats=want_stats)
 
 
 class CrossAttention(nn.Module, Packed):
@@ -318,13 +328,21 @@ class CrossAttention(nn.Module, Packed):
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
         self.backend = backend
 
-    def attend(self, x, context=None, kv=None):
-        """x: [B, T, C] bf16 -> attention output before to_out, [B, T, inner].  `kv`: precomputed [B, Tk, 2*inner]."""
+    def attend(self, x, context=None, kv=None, ln=None):
+        """x: [B, T, C] bf16 -> attention output before to_out, [B, T, inner].  `kv`: precomputed [B, Tk, 2*inner].
+        `ln` (self-attention only) = (LayerNorm, RowStats of x): the norm is folded into the QKV GEMM."""
         inner = self.to_q.weight.shape[0]
         if context is None:
-            w = self._pk("qkv", (self.to_q.weight, self.to_k.weight, self.to_v.weight),
-                         lambda q, k, v: torch.cat([q, k, v], 0).to(bf16).contiguous())
-            qkv = ops.gemm(x, w)
+            if ln is not None:
+                norm, stats = ln
+                w, colsum, shift = self._pk(
+                    "qkv_ln", (self.to_q.weight, self.to_k.weight, self.to_v.weight, norm.weight, norm.bias),
+                    lambda q, k, v, g, b: ops.pack_linear_ln(torch.cat([q, k, v], 0), g, b))
+                qkv = ops.gemm(x, w, ln=(stats, colsum, shift, norm.eps))
+            else:
+                w = self._pk("qkv", (self.to_q.weight, self.to_k.weight, self.to_v.weight),
+                             lambda q, k, v: torch.cat([q, k, v], 0).to(bf16).contiguous())
+                qkv = ops.gemm(x, w)
             return ops.attention(qkv, qkv, qkv, self.heads, q_col=0, k_col=inner, v_col=2 * inner, scale=self.scale)
         q = _linear(self, "q", self.to_q, x)
         bound = self._bound_entry(context)
@@ -345,9 +363,17 @@ class CrossAttention(nn.Module, Packed):
     def _wkv(self):
         return self._pk("kv", (self.to_k.weight, self.to_v.weight), lambda k, v: torch.cat([k, v], 0).to(bf16).contiguous())
 
+    def _fold_norm(self) -> Optional[nn.LayerNorm]:
+        """The LayerNorm in front of this attention (set by BasicTransformerBlock) when it is to be folded into the
+        bound keys, else None."""
+        return self.__dict__.get("_pre_norm") if FUSE_LN_INTO_GEMM else None
+
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in (self.to_q.weight, self.to_k.weight, self.to_v.weight,
-                                                          self.to_out[0].weight))
+        ps = [self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_out[0].weight]
+        norm = self._fold_norm()
+        if norm is not None:
+            ps += [norm.weight, norm.bias]
+        return tuple((p.data_ptr(), p._version) for p in ps)
 
     def _bound_entry(self, context):
         """The (context, kv, folded, weights_key) entry bound for this very tensor object, or None.  An entry made
@@ -382,7 +408,7 @@ class CrossAttention(nn.Module, Packed):
         same = old is not None and old[0] is context and tuple(old[1].shape) == shape
         kv = ops.gemm(context, self._wkv(), out=old[1] if same else None)
         fused = self._fold_projections(context)
-        if same and old[2] is not None and fused is not None:
+        if same and old[2] is not None and fused is not None and len(old[2]) == len(fused):
             for dst, src in zip(old[2], fused):
                 dst.copy_(src)
             fused = old[2]
@@ -394,7 +420,7 @@ class CrossAttention(nn.Module, Packed):
         e = self.__dict__.get("_static", {}).get(id(context))
         if e is None or e[0] is not context:
             return []
-        return [e[1]] + ([e[2][0], e[2][1]] if e[2] is not None else [])
+        return [e[1]] + ([t for t in e[2] if t.is_cuda or t.dim() > 0] if e[2] is not None else [])
 
     SEG = 80  # key slots per head in the folded form (77 text tokens, padded)
 
@@ -404,7 +430,10 @@ class CrossAttention(nn.Module, Packed):
             softmax(x Wq^T K_h^T * s) V_h Wo_h^T  =  softmax(x K'_h^T) V'_h,   K'_h = s K_h Wq_h,  V'_h = V_h Wo_h^T
         so a cross-attention is two GEMMs (the first with a per-head softmax epilogue) instead of q-projection +
         attention + out-projection.  One-time fp32 preparation per bound context, like weight packing.
-        Returns (K' [B, H*80, C] bf16 in log2 units, V'^T [B, C, H*80] bf16, number of keys) or None."""
+        Returns (K' [B, H*80, C] bf16 in log2 units, V'^T [B, C, H*80] bf16, number of keys) or None.
+        With a LayerNorm to fold (`_fold_norm`) K' additionally absorbs its gain, and two more tensors follow: the column
+        sums of the rounded K' gamma and the shift K' beta, both [B, H*80] fp32 (ops.gemm's `ln` operands):
+            LN(x) K'^T = rstd * (x (K' gamma)^T - mean * colsum) + K' beta."""
         b, tk = context.shape[0], context.shape[1]
         if context.dim() != 3 or tk > self.SEG:
             return None
@@ -418,28 +447,49 @@ class CrossAttention(nn.Module, Packed):
         kp[:, :, :tk] = torch.einsum("bjhd,hdc->bhjc", k, wq) * (self.scale * 1.4426950408889634)
         vp = torch.zeros(b, h, self.SEG, wo.shape[0], device=context.device)
         vp[:, :, :tk] = torch.einsum("bjhd,chd->bhjc", v, wo)
-        return (kp.reshape(b, h * self.SEG, c).to(bf16).contiguous(),
-                vp.reshape(b, h * self.SEG, -1).transpose(1, 2).to(bf16).contiguous(),
-                torch.tensor(tk))
+        kp = kp.reshape(b, h * self.SEG, c)
+        vpt = vp.reshape(b, h * self.SEG, -1).transpose(1, 2).to(bf16).contiguous()
+        norm = self._fold_norm()
+        if norm is None:
+            return (kp.to(bf16).contiguous(), vpt, torch.tensor(tk))
+        kg = (kp * norm.weight.float()).to(bf16).contiguous()
+        return (kg, vpt, torch.tensor(tk), kg.float().sum(-1).contiguous(), (kp @ norm.bias.float()).contiguous())
 
     def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
-                residual: Optional[torch.Tensor] = None, alpha: float = 1.0, kv: Optional[torch.Tensor] = None):
+                residual: Optional[torch.Tensor] = None, alpha: float = 1.0, kv: Optional[torch.Tensor] = None,
+                ln=None, want_stats: bool = False):
+        """`ln` = (LayerNorm, RowStats of x): x is the RAW residual stream; the norm is folded into the first GEMM
+        (QKV projection, or the folded-key product of a bound context) where that exists, otherwise applied by the
+        LayerNorm kernel here.  `want_stats`: return (out, RowStats of out) for the next folded norm."""
         if mask is not None or additional_tokens is not None or n_times_crossframe_attn_in_self:
             raise NotImplementedError("masks / additional tokens / cross-frame attention are not on the hot path")
         x = tokens_bf16(x)
         ctx = tokens_bf16(context) if context is not None else None
         if ctx is not None and kv is None and x.dim() == 3 and x.shape[1] % 256 == 0:
             bound = self._bound_entry(ctx)
+            folds_ln = bound is not None and bound[2] is not None and len(bound[2]) == 5
+            if folds_ln and (ln is None or ln[0] is not self._fold_norm()):
+                bound = None    # the bound keys carry a LayerNorm this call does not ask for: take the general path
             if bound is not None and bound[2] is not None and x.shape[0] % bound[2][0].shape[0] == 0:
                 # The bound context may have fewer rows than x: [uncond; cond] captions shared by several latents
                 # (tiles of one image batched into one step).  Rows of x are ordered [uncond x n; cond x n], so
                 # each context row serves a contiguous block of n * T query rows.
-                k_fold, v_fold, tk = bound[2]
+                k_fold, v_fold, tk = bound[2][:3]
                 rpg = x.shape[1] * (x.shape[0] // k_fold.shape[0])
-                p = ops.gemm(x, k_fold, softmax_valid=int(tk), w_rows_per_group=rpg)
+                if folds_ln:
+                    p = ops.gemm(x, k_fold, softmax_valid=int(tk), w_rows_per_group=rpg,
+                                 ln=(ln[1], bound[2][3], bound[2][4], ln[0].eps))
+                else:
+                    if ln is not None:
+                        x = ops.layer_norm(x, ln[0].weight, ln[0].bias, ln[0].eps)
+                    p = ops.gemm(x, k_fold, softmax_valid=int(tk), w_rows_per_group=rpg)
                 bias = self._pk("out.b", (self.to_out[0].bias,), _F32)
-                return ops.gemm(p, v_fold, bias, residual=residual, alpha=alpha, w_rows_per_group=rpg)
-        return _linear(self, "out", self.to_out[0], self.attend(x, ctx, kv), residual=residual, alpha=alpha)
+                return ops.gemm(p, v_fold, bias, residual=residual, alpha=alpha, w_rows_per_group=rpg,
+                                want_stats=want_stats)
+        if ln is not None and ctx is not None:
+            x, ln = ops.layer_norm(x, ln[0].weight, ln[0].bias, ln[0].eps), None
+        return _linear(self, "out", self.to_out[0], self.attend(x, ctx, kv, ln=ln), residual=residual, alpha=alpha,
+                       want_stats=want_stats)
 
 
 MemoryEfficientCrossAttention = CrossAttention  # attention.py:288-373 computes the same function
@@ -459,16 +509,26 @@ class BasicTransformerBlock(nn.Module):
                                     dropout=dropout)
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
         self.checkpoint = checkpoint
+        self.attn2.__dict__["_pre_norm"] = self.norm2   # not a submodule of attn2: folded into its bound keys
 
     @staticmethod
     def _ln(norm: nn.LayerNorm, x):
         return ops.layer_norm(x, norm.weight, norm.bias, norm.eps)
 
-    def forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0):
+    def forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0, stats=None,
+                want_stats: bool = False):
+        """`stats`: RowStats of x written by the GEMM that produced it.  With them no LayerNorm kernel runs: each norm is
+        folded into the GEMM behind it and every residual GEMM hands the statistics of its output to the next one
+        (DESIGN.md section 4).  `want_stats`: return (x, RowStats) for the next block."""
         x = tokens_bf16(x)
-        x = self.attn1(self._ln(self.norm1, x), context=context if self.disable_self_attn else None, residual=x)
-        x = self.attn2(self._ln(self.norm2, x), context=context, residual=x)
-        return self.ff(self._ln(self.norm3, x), residual=x)
+        if stats is None:
+            x = self.attn1(self._ln(self.norm1, x), context=context if self.disable_self_attn else None, residual=x)
+            x = self.attn2(self._ln(self.norm2, x), context=context, residual=x)
+            return self.ff(self._ln(self.norm3, x), residual=x, want_stats=want_stats)
+        x, stats = self.attn1(x, context=context if self.disable_self_attn else None, residual=x,
+                              ln=(self.norm1, stats), want_stats=True)
+        x, stats = self.attn2(x, context=context, residual=x, ln=(self.norm2, stats), want_stats=True)
+        return self.ff(x, residual=x, ln=(self.norm3, stats), want_stats=want_stats)
 
 
 class SpatialTransformer(nn.Module, Packed):
@@ -505,9 +565,16 @@ class SpatialTransformer(nn.Module, Packed):
         context = [tokens_bf16(c) if c is not None else None for c in context]
         b, h, w, c = x.shape
         t = _gn(self.norm, x).view(b, h * w, c)
-        t = _linear(self, "proj_in", self.proj_in, t)
+        stats = None
+        if FUSE_LN_INTO_GEMM:
+            t, stats = _linear(self, "proj_in", self.proj_in, t, want_stats=True)
+        else:
+            t = _linear(self, "proj_in", self.proj_in, t)
+        last = len(self.transformer_blocks) - 1
         for i, block in enumerate(self.transformer_blocks):
-            t = block(t, context=context[i if len(context) > 1 else 0])
+            r = block(t, context=context[i if len(context) > 1 else 0], stats=stats,
+                      want_stats=stats is not None and i < last)
+            t, stats = r if isinstance(r, tuple) else (r, None)
         t = _linear(self, "proj_out", self.proj_out, t, residual=x.view(b, h * w, c))
         return t.view(b, h, w, c)
 

@@ -160,6 +160,47 @@ def pack_geglu(weight: torch.Tensor, bias: torch.Tensor):
     return weight.detach()[idx].to(bf16).contiguous(), bias.detach()[idx].float().contiguous()
 
 
+def pack_linear_ln(weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """Operands of ``gemm(..., ln=...)`` for Linear(LayerNorm(x)): (W' = W * gamma as bf16 [N, K], colsum [1, N] of the
+    ROUNDED W' so the mean term cancels exactly what the tensor cores accumulate, shift = W beta + bias [1, N])."""
+    w32 = weight.detach().float()
+    wp = (w32 * gamma.detach().float()[None, :]).to(bf16).contiguous()
+    shift = w32 @ beta.detach().float()
+    if bias is not None:
+        shift = shift + bias.detach().float()
+    return wp, wp.float().sum(1)[None].contiguous(), shift[None].contiguous()
+
+
+def pack_geglu_ln(weight: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """pack_linear_ln for the GEGLU projection: rows interleaved as pack_geglu does."""
+    idx = geglu_interleave_index(weight.shape[0] // 2, weight.device)
+    return pack_linear_ln(weight.detach()[idx], gamma, beta, bias.detach()[idx])
+
+
+class RowStats:
+    """Per-row partial (sum, sum of squares) of a bf16 [M, N] GEMM output, one pair per N tile of the GEMM that wrote it:
+    buf [parts, M, 2] fp32.  Consumed by ``gemm(..., ln=(stats, colsum, shift, eps))``."""
+
+    __slots__ = ("buf", "parts", "dim")
+
+    def __init__(self, buf: torch.Tensor, parts: int, dim: int):
+        self.buf, self.parts, self.dim = buf, parts, dim
+
+
+_n_tile_cache: dict = {}
+
+
+def gemm_n_tile(M: int, N: int, K: int) -> int:
+    key = (M, N, K)
+    t = _n_tile_cache.get(key)
+    if t is None:
+        t = _lib.load().b200sr_gemm_n_tile(M, N, K)
+        if t <= 0:
+            raise _lib.B200SRError(f"gemm_n_tile({M}, {N}, {K}) = {t}")
+        _n_tile_cache[key] = t
+    return t
+
+
 # ------------------------------------------------------------------------------------------------
 # dense contractions
 # ------------------------------------------------------------------------------------------------
@@ -202,7 +243,9 @@ def gemm(
     softmax_valid: int = 0,
     w_rows_per_group: int = 0,
     w_dynamic: bool = False,
-) -> torch.Tensor:
+    ln=None,
+    want_stats: bool = False,
+):
     """``out = alpha * (a @ w.T + bias) + rowvec[group] + residual`` (or GEGLU).  a: [..., K] bf16
     (last-dim contiguous, uniform row stride), w: [N, K] packed bf16.  `out` may be a column
     slice of a wider row-major tensor (its row stride is honoured).
@@ -210,7 +253,10 @@ def gemm(
     operands).  `softmax_valid` > 0: the epilogue is a row softmax (base 2, no scale) over each 80-column segment
     of which the first `softmax_valid` columns take part; output bf16 probabilities.
     `w_dynamic`: w was written by an earlier kernel on this stream (an activation used as the B operand): the
-    kernel then must not prefetch it ahead of its programmatic dependency."""
+    kernel then must not prefetch it ahead of its programmatic dependency.
+    `ln` = (RowStats of a, colsum, shift, eps): a holds RAW rows and the LayerNorm in front of the Linear is folded into
+    the epilogue (operands from pack_linear_ln; colsum / shift are [G, N] with per-group weights).
+    `want_stats`: also return the RowStats of the bf16 output -> (out, stats)."""
     _req(w, bf16, "gemm.w")
     if a.dtype != bf16 or not a.is_cuda:
         raise _lib.B200SRError("gemm.a: expected CUDA bf16")
@@ -237,10 +283,28 @@ def gemm(
         ldr = r2.stride(0)
     e = _epilogue(o2, ldc, bias, rowvec, rows_per_group, residual, ldr, out_fp32, geglu, alpha, act,
                   softmax_valid, w_rows_per_group, w_group_stride, w_dynamic)
-    with _Timed("gemm", 2.0 * M * N * K, f"M{M} N{N} K{K}{' geglu' if geglu else ''}"):
+    if ln is not None:
+        st, colsum, shift, eps = ln
+        groups = w.shape[0] if w_rows_per_group else 1
+        if st.buf.shape[1] != M or st.dim != K:
+            raise _lib.B200SRError(f"gemm.ln: statistics of a [{st.buf.shape[1]}, {st.dim}] matrix, a is [{M}, {K}]")
+        for t, nme in ((colsum, "colsum"), (shift, "shift")):
+            _req(t, torch.float32, f"gemm.ln.{nme}")
+            if t.numel() != groups * N:
+                raise _lib.B200SRError(f"gemm.ln.{nme}: expected [{groups}, {N}]")
+        e.ln_stats, e.ln_parts, e.ln_colsum, e.ln_shift, e.ln_eps = st.buf.data_ptr(), st.parts, colsum.data_ptr(), \
+            shift.data_ptr(), float(eps)
+    stats = None
+    if want_stats:
+        if geglu or softmax_valid or out_fp32:
+            raise _lib.B200SRError("gemm.want_stats: plain bf16 output only")
+        parts = -(-N // (force_bn if force_bn > 0 else gemm_n_tile(M, N, K)))
+        stats = RowStats(torch.empty(parts, M, 2, dtype=torch.float32, device=a.device), parts, N)
+        e.ln_stats_out = stats.buf.data_ptr()
+    with _Timed("gemm", 2.0 * M * N * K, f"M{M} N{N} K{K}{' geglu' if geglu else ''}{' ln' if ln is not None else ''}"):
         rc = _lib.load().b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), force_bn, _stream())
     check(rc, f"gemm M={M} N={N} K={K}")
-    return out
+    return (out, stats) if want_stats else out
 
 
 def conv3x3(

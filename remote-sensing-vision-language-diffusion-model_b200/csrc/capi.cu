@@ -81,6 +81,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, 
               cudaStream_t stream);
 int conv3x3_bf16(const void* x, const void* w, int NB, int H, int W, int Cin, int Cout, int stride, int pad_lo,
                  const EpilogueArgs& e, int force_bn, cudaStream_t stream);
+int gemm_n_tile(int M, int N, int K);
 int pointwise_small(const void* x, const float* w, const float* bias, void* y, int Cin, int Cout, long long rows, int HW,
                     int out_nchw_f32, float scale, cudaStream_t stream);
 int diag_gaussian(const float* moments, const float* noise, float* z, int N, int C, int HW, float scale,
@@ -158,6 +159,12 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.a_gn_bias = e->a_gn_bias;
   a.a_gn_groups = e->a_gn_groups;
   a.a_gn_silu = e->a_gn_silu;
+  a.ln_stats = e->ln_stats;
+  a.ln_parts = e->ln_parts;
+  a.ln_colsum = e->ln_colsum;
+  a.ln_shift = e->ln_shift;
+  a.ln_eps = e->ln_eps;
+  a.ln_stats_out = e->ln_stats_out;
   return a;
 }
 
@@ -168,7 +175,7 @@ using namespace b200sr;
 
 extern "C" {
 
-int b200sr_abi_version(void) { return 3; }
+int b200sr_abi_version(void) { return 4; }
 int b200sr_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200SR_ENODEV;
@@ -181,6 +188,7 @@ int b200sr_gemm_bf16(const void* A, int64_t lda, const void* W, int32_t M, int32
   if (A == nullptr || W == nullptr || epi == nullptr) return B200SR_EINVAL;
   return gemm_bf16(A, lda, W, M, N, K, to_args(epi), force_bn, S(stream));
 }
+int b200sr_gemm_n_tile(int32_t M, int32_t N, int32_t K) { return gemm_n_tile(M, N, K); }
 int b200sr_conv3x3_bf16(const void* x, const void* w, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                         int32_t stride, int32_t pad_lo, const b200sr_epilogue* epi, int32_t force_bn, void* stream) {
   if (x == nullptr || w == nullptr || epi == nullptr) return B200SR_EINVAL;

@@ -377,6 +377,12 @@ struct EpilogueArgs {
   const float* a_gn_weight;
   const float* a_gn_bias;
   int a_gn_groups, a_gn_silu;
+  const float* ln_stats;    // GEMM only: LayerNorm of the A rows folded into the epilogue (see include/b200sr.h)
+  int ln_parts;
+  const float* ln_colsum;
+  const float* ln_shift;
+  float ln_eps;
+  float* ln_stats_out;      // GEMM only: per-row partial (sum, sum of squares) of the stored bf16 output, [n tiles][M][2]
 };
 
 }  // namespace b200sr

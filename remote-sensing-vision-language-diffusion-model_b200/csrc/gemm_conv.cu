@@ -111,9 +111,40 @@ struct GemmParams {
   const float* gn_weight;  // [Cin]
   const float* gn_bias;    // [Cin]
   int gn_groups, gn_silu;
+  // mode 0, LayerNorm folded around the GEMM (see b200sr_epilogue in include/b200sr.h):
+  //   consumer  v = rstd[m] * (acc[m, n] - mean[m] * colsum[g, n]) + shift[g, n]   with (mean, rstd) folded from ln_parts
+  //             per-row partial (sum, sum of squares) written by the GEMM that produced A
+  //   producer  ln_stats_out[n_blk][m] = (sum, sum of squares) of the bf16 values this tile stores in row m
+  const float2* ln_stats;   // [ln_parts][M], nullptr = off
+  int ln_parts;
+  const float* ln_colsum;   // [weight groups][N]
+  const float* ln_shift;    // [weight groups][N]
+  float ln_eps;
+  float2* ln_stats_out;     // [num_n_blocks][M], nullptr = off
 };
 
 static constexpr int SOFTMAX_SEG = 80;  // columns per head segment in the softmax epilogue (77 text tokens, padded)
+
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): the LayerNorm-fold epilogue's extra arithmetic at half the issue slots.
+//   v = rstd * v + (nm * c + b)   for two columns
+__device__ __forceinline__ void ln_apply2(float& v0, float& v1, float rstd, float nm, float c0, float c1, float b0, float b1) {
+  asm("{\n\t.reg .b64 vv, rr, nn, cc, bb;\n\t"
+      "mov.b64 vv, {%0, %1};\n\tmov.b64 rr, {%2, %2};\n\tmov.b64 nn, {%3, %3};\n\t"
+      "mov.b64 cc, {%4, %5};\n\tmov.b64 bb, {%6, %7};\n\t"
+      "fma.rn.f32x2 bb, nn, cc, bb;\n\tfma.rn.f32x2 vv, rr, vv, bb;\n\t"
+      "mov.b64 {%0, %1}, vv;\n\t}"
+      : "+f"(v0), "+f"(v1)
+      : "f"(rstd), "f"(nm), "f"(c0), "f"(c1), "f"(b0), "f"(b1));
+}
+//   s1 += (v0, v1);  s2 += (v0^2, v1^2)
+__device__ __forceinline__ void stats_acc2(float2& s1, float2& s2, float v0, float v1) {
+  asm("{\n\t.reg .b64 vv, a1, a2;\n\t"
+      "mov.b64 vv, {%4, %5};\n\tmov.b64 a1, {%0, %1};\n\tmov.b64 a2, {%2, %3};\n\t"
+      "add.rn.f32x2 a1, a1, vv;\n\tfma.rn.f32x2 a2, vv, vv, a2;\n\t"
+      "mov.b64 {%0, %1}, a1;\n\tmov.b64 {%2, %3}, a2;\n\t}"
+      : "+f"(s1.x), "+f"(s1.y), "+f"(s2.x), "+f"(s2.y)
+      : "f"(v0), "f"(v1));
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -187,7 +218,9 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
 
 // kXform: the instantiation with the extra GroupNorm warps (320 threads, <= 204 registers); the plain one keeps 192
 // threads and the full register budget its epilogues want.
-template <int kCluster, bool kXform>
+// kLn: the instantiation whose epilogue folds a LayerNorm around the GEMM (row statistics in and / or out); kept apart so
+// the plain kernel's register allocation (233, no spills) does not change.
+template <int kCluster, bool kXform, bool kLn = false>
 __global__ void __launch_bounds__(kXform ? GEMM_THREADS_XFORM : GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -685,6 +718,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sub = warp & 3;           // TMEM sub-partition this warp may access
     const int r = sub * 32 + lane;      // accumulator row == TMEM lane
     float* s_bias = s_epi + (warp - 2) * 256;
+    const bool ln_in = kLn && p.ln_stats != nullptr;
+    const bool ln_out = kLn && p.ln_stats_out != nullptr;
+    float* s_col = s_ab + (warp - 2) * 256;   // LayerNorm fold: column sums of the weight tile (the fused-GN table is mode 3 only)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = work0; work < num_work; work += work_stride) {
@@ -712,15 +748,62 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // stage bias[n0 .. n0+BN) (zero beyond N) — constant data, independent of earlier kernels
       __syncwarp();
-      for (int j = lane; j < p.BN; j += 32)
-        s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-      __syncwarp();
       const bool has_res = p.residual != nullptr && valid;
       const __nv_bfloat16* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
-      const float* rv_row = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
+      const float* rv_row = (!kLn && p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
       uint4 res_cur[4], res_nxt[4];
-      if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
-      if (has_res) {
+      float ln_rstd = 1.f, ln_nm = 0.f;  // v = rstd * acc - mean * rstd * colsum + shift
+      if (!ln_in) {
+        for (int j = lane; j < p.BN; j += 32)
+          s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        __syncwarp();
+        if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
+      } else {
+        // Every global load of the tile's prologue is issued before the first use of any of them: with several tiles per
+        // CTA the epilogue is the longer pipeline stage, and three dependent L2 round trips per tile showed as +25 %
+        // kernel time (profiles/r02_ln_fold.txt).
+        const long long wg =
+            p.w_rows_per_group > 0 ? (static_cast<long long>(m_blk) * BLOCK_M / p.w_rows_per_group) * p.N : 0;
+        float bb[8], cc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = lane + 32 * i;
+          const bool in = j < p.BN && n0 + j < p.N;
+          bb[i] = (in && p.bias != nullptr) ? __ldg(p.bias + n0 + j) : 0.f;
+          cc[i] = in ? __ldg(p.ln_colsum + wg + n0 + j) : 0.f;
+          bb[i] += in ? __ldg(p.ln_shift + wg + n0 + j) : 0.f;
+        }
+        if (work == work0) pdl_wait();  // residual / row statistics come from earlier kernels
+        float s1 = 0.f, s2 = 0.f;
+        if (valid) {
+          for (int q = 0; q < p.ln_parts; ++q) {
+            const float2 t = __ldg(p.ln_stats + static_cast<long long>(q) * p.M + row);
+            s1 += t.x;
+            s2 += t.y;
+          }
+        }
+        if (has_res) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = lane + 32 * i;
+          if (j < p.BN) {
+            s_bias[j] = bb[i];
+            s_col[j] = cc[i];
+          }
+        }
+        __syncwarp();
+        const float inv_k = 1.0f / static_cast<float>(p.K);
+        const float mean = s1 * inv_k;
+        const float var = fmaxf(s2 * inv_k - mean * mean, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_nm = -mean * ln_rstd;
+      }
+      float2 ln_acc1 = make_float2(0.f, 0.f), ln_acc2 = make_float2(0.f, 0.f);  // producer side: (sum, sum of squares), 2 lanes
+      if (has_res && !ln_in) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
@@ -748,6 +831,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[64 + j] = __uint_as_float(a2[j]);
+          if (ln_in) {
+#pragma unroll
+            for (int j = 0; j < SOFTMAX_SEG; j += 4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(s_col + sg * SOFTMAX_SEG + j);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sg * SOFTMAX_SEG + j);
+              ln_apply2(v[j], v[j + 1], ln_rstd, ln_nm, c4.x, c4.y, b4.x, b4.y);
+              ln_apply2(v[j + 2], v[j + 3], ln_rstd, ln_nm, c4.z, c4.w, b4.z, b4.w);
+            }
+          }
           float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < SOFTMAX_SEG; ++j) {
@@ -798,10 +890,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + j);
-            v[j] = __uint_as_float(a_cur[j]) + b4.x;
-            v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
-            v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
+            if (ln_in) {
+              const float4 c4 = *reinterpret_cast<const float4*>(s_col + c + j);
+              v[j] = __uint_as_float(a_cur[j]);
+              v[j + 1] = __uint_as_float(a_cur[j + 1]);
+              v[j + 2] = __uint_as_float(a_cur[j + 2]);
+              v[j + 3] = __uint_as_float(a_cur[j + 3]);
+              ln_apply2(v[j], v[j + 1], ln_rstd, ln_nm, c4.x, c4.y, b4.x, b4.y);
+              ln_apply2(v[j + 2], v[j + 3], ln_rstd, ln_nm, c4.z, c4.w, b4.z, b4.w);
+            } else {
+              v[j] = __uint_as_float(a_cur[j]) + b4.x;
+              v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
+              v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
+              v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
+            }
           }
           if (!kXform && p.geglu) {
             // columns [0,16) = value, [16,32) = gate of the same 16 output features
@@ -853,7 +955,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[q * 8 + 7] += f3.y;
               }
             }
-            if (p.act == 1) {
+            if (kLn) {
+              // no activation in the LayerNorm-folding instantiation (register budget)
+            } else if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             } else if (p.act == 2) {   // exact (erf) GELU: OpenCLIP text tower MLP
@@ -863,7 +967,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = quick_gelu_f(v[j]);
             }
-            if (!kXform && p.out_fp32) {
+            if (!kXform && !kLn && p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -881,6 +985,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
                   u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
                   reinterpret_cast<uint4*>(dst)[q] = u;
+                  if (ln_out) {
+                    // Statistics of the fp32 values before their rounding to bf16 (the rounding errors average out over
+                    // the row: the mean moves by ~2^-9 |x| / sqrt(N)), two columns per packed fp32 instruction.
+#pragma unroll
+                    for (int t = 0; t < 8; t += 2) stats_acc2(ln_acc1, ln_acc2, v[q * 8 + t], v[q * 8 + t + 1]);
+                  }
                 }
               }
             }
@@ -893,6 +1003,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int q = 0; q < 4; ++q) res_cur[q] = res_nxt[q];
         }
       }
+      if (ln_out && valid)
+        p.ln_stats_out[static_cast<long long>(n_blk) * p.M + row] = make_float2(ln_acc1.x + ln_acc1.y, ln_acc2.x + ln_acc2.y);
       // release this accumulator stage back to the MMA warp
       if (threadIdx.x == 64) GT(10);
       tc_fence_before();
@@ -970,7 +1082,8 @@ static long long* g_gemm_trace = nullptr;
 
 template <int kCluster>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int xform_bytes = p.gn_stats != nullptr ? ((p.Cin * 8 + 1023) / 1024) * 1024 : 0;   // per-channel (a, b) of one image
+  // per-channel (a, b) of one image (fused GroupNorm, mode 3) or the weight tile's column sums (LayerNorm fold, mode 0)
+  const int xform_bytes = p.gn_stats != nullptr ? ((p.Cin * 8 + 1023) / 1024) * 1024 : (p.ln_stats != nullptr ? 4096 : 0);
   const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/ - xform_bytes;
   const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
   const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
@@ -1005,6 +1118,8 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
   if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess ||
+        cudaFuncSetAttribute(gemm_conv_kernel<kCluster, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_conv_kernel<kCluster, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess)
       return B200SR_ELAUNCH;
@@ -1016,6 +1131,9 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
       p.gn_stats != nullptr
           ? launch_k(gemm_conv_kernel<kCluster, true>, dim3(grid), dim3(GEMM_THREADS_XFORM), smem_bytes, stream, kCluster, tmA,
                      tmB, p)
+      : (p.ln_stats != nullptr || p.ln_stats_out != nullptr)
+          ? launch_k(gemm_conv_kernel<kCluster, false, true>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, kCluster,
+                     tmA, tmB, p)
           : launch_k(gemm_conv_kernel<kCluster, false>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, kCluster, tmA, tmB,
                      p);
   return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
@@ -1044,6 +1162,19 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.gn_bias = e.a_gn_bias;
   p.gn_groups = e.a_gn_groups;
   p.gn_silu = e.a_gn_silu;
+  p.ln_stats = reinterpret_cast<const float2*>(e.ln_stats);
+  p.ln_parts = e.ln_parts;
+  p.ln_colsum = e.ln_colsum;
+  p.ln_shift = e.ln_shift;
+  p.ln_eps = e.ln_eps;
+  p.ln_stats_out = reinterpret_cast<float2*>(e.ln_stats_out);
+  if (e.ln_stats != nullptr &&
+      (p.mode != 0 || e.ln_parts <= 0 || e.ln_colsum == nullptr || e.ln_shift == nullptr || e.a_gn_stats != nullptr))
+    return B200SR_EINVAL;
+  if (e.ln_stats_out != nullptr && (p.mode != 0 || e.geglu || e.softmax_valid > 0)) return B200SR_EINVAL;
+  // the LayerNorm-folding instantiation carries bias, alpha, residual, geglu and the softmax only
+  if ((e.ln_stats != nullptr || e.ln_stats_out != nullptr) && (e.out_fp32 || e.rowvec != nullptr || e.act != 0))
+    return B200SR_EINVAL;
   if (e.a_gn_stats != nullptr) {
     // fused input GroupNorm: halo convolution only, affine parameters required
     if (p.mode != 3 || e.a_gn_weight == nullptr || e.a_gn_bias == nullptr || e.a_gn_groups <= 0 ||
@@ -1087,6 +1218,14 @@ static int finish(const CUtensorMap& tmA, const void* W, GemmParams& p, int real
   const int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
   if (rc) return rc;
   return cluster == 2 ? launch_t<2>(tmA, tmB, p, stream) : launch_t<1>(tmA, tmB, p, stream);
+}
+
+// The N tile gemm_bf16 picks for a plain GEMM (no softmax epilogue, force_bn = 0): a GEMM that writes row statistics
+// writes ceil(N / tile) partials per row, which the consuming GEMM has to be told.
+int gemm_n_tile(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  return pick_bn(m_blocks, N, (K + BLOCK_K - 1) / BLOCK_K, num_sms(), m_blocks >= 2 ? 2 : 1);
 }
 
 int gemm_bf16(const void* A, long long lda, const void* W, int M, int N, int K, const EpilogueArgs& e, int force_bn,

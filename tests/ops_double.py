@@ -22,13 +22,23 @@ def require_cuda(t, what):
 
 
 def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu=False, alpha=1.0, act=0, out=None,
-         out_fp32=False, force_bn=0, softmax_valid=0, w_rows_per_group=0, w_dynamic=False):
+         out_fp32=False, force_bn=0, softmax_valid=0, w_rows_per_group=0, w_dynamic=False, ln=None, want_stats=False):
     a2 = a.float().reshape(-1, a.shape[-1])
+    n_groups = (a2.shape[0] + w_rows_per_group - 1) // w_rows_per_group if w_rows_per_group else 1
     if w_rows_per_group:
-        y = torch.cat([a2[g * w_rows_per_group:(g + 1) * w_rows_per_group] @ w[g].float().t()
-                       for g in range((a2.shape[0] + w_rows_per_group - 1) // w_rows_per_group)], 0)
+        y = torch.cat([a2[g * w_rows_per_group:(g + 1) * w_rows_per_group] @ w[g].float().t() for g in range(n_groups)], 0)
     else:
         y = a2 @ w.float().t()
+    if ln is not None:
+        # the library's arithmetic: statistics from the producer's partial sums, applied around the raw product
+        st, colsum, shift, eps = ln
+        assert st.buf.shape[1] == a2.shape[0] and st.dim == a2.shape[1]
+        tot = st.buf.sum(0)
+        mean = tot[:, 0] / st.dim
+        rstd = torch.rsqrt((tot[:, 1] / st.dim - mean * mean).clamp_min(0) + eps)
+        gidx = torch.arange(a2.shape[0]) // w_rows_per_group if w_rows_per_group else torch.zeros(a2.shape[0], dtype=torch.long)
+        cs, sh = colsum.reshape(n_groups, -1)[gidx], shift.reshape(n_groups, -1)[gidx]
+        y = rstd[:, None] * (y - mean[:, None] * cs) + sh
     if softmax_valid:
         seg = y.view(y.shape[0], -1, 80).clone()
         seg[:, :, softmax_valid:] = float("-inf")
@@ -54,10 +64,22 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu
             y = y * torch.sigmoid(1.702 * y)
     y = y.reshape(*a.shape[:-1], y.shape[-1])
     y = y if out_fp32 else y.to(bf16)
+    stats = None
+    if want_stats:
+        # two column tiles, like a GEMM whose N tile is half the row
+        y2 = y.float().reshape(-1, y.shape[-1])
+        half = (y2.shape[1] // 2 + 7) // 8 * 8
+        parts = [y2[:, :half], y2[:, half:]]
+        stats = RowStats(torch.stack([torch.stack([p.sum(1), (p * p).sum(1)], -1) for p in parts]), 2, y2.shape[1])
     if out is not None:
         out.copy_(y.reshape(out.shape))
-        return out
-    return y
+        y = out
+    return (y, stats) if want_stats else y
+
+
+class RowStats:
+    def __init__(self, buf, parts, dim):
+        self.buf, self.parts, self.dim = buf, parts, dim
 
 
 def conv3x3_gn_fusable(x, stride=1, cout=None):

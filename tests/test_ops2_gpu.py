@@ -103,3 +103,94 @@ def test_conv3x3_with_fused_input_groupnorm(n, h, w, cin, cout, extras):
     assert rel_l2(fused, ref) < 5e-3
     mean = xf.reshape(n, 32, -1).mean(-1)
     assert torch.allclose(stats[..., 0], mean, atol=2e-3)
+
+
+def _row_stats_ref(y):
+    y = y.float().reshape(-1, y.shape[-1])
+    return y.mean(1), y.var(1, unbiased=False)
+
+
+@pytest.mark.parametrize("m,k,n", [(2048, 1280, 1280), (8192, 640, 640), (300, 320, 200)])
+def test_gemm_row_statistics_of_the_output(m, k, n):
+    """want_stats: the per-N-tile partial (sum, sum of squares) of the output rows fold to the rows' mean / variance."""
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    a = torch.randn(m, k, generator=g, device="cuda").to(bf16)
+    w = (torch.randn(n, k, generator=g, device="cuda") * k ** -0.5).to(bf16)
+    b = torch.randn(n, generator=g, device="cuda")
+    res = (torch.randn(m, n, generator=g, device="cuda") * 3 + 1.5).to(bf16)
+    plain = ops.gemm(a, w, b, residual=res)
+    y, st = ops.gemm(a, w, b, residual=res, want_stats=True)
+    assert torch.equal(y, plain)                                   # same arithmetic with or without the statistics
+    assert st.parts == -(-n // ops.gemm_n_tile(m, n, k)) and st.buf.shape == (st.parts, m, 2) and st.dim == n
+    tot = st.buf.sum(0)
+    mean, var = _row_stats_ref(y)
+    # the kernel sums the fp32 values before their rounding to bf16: |mean error| ~ 2^-9 |x| / sqrt(n)
+    assert torch.allclose(tot[:, 0] / n, mean, atol=2e-3, rtol=1e-3)
+    assert torch.allclose(tot[:, 1] / n - (tot[:, 0] / n) ** 2, var, atol=2e-2, rtol=2e-3)
+
+
+@pytest.mark.parametrize("m,c,n,kind", [(2048, 1280, 3840, "plain"), (8192, 640, 1920, "plain"), (2048, 1280, 10240, "geglu"),
+                                        (8192, 640, 5120, "geglu"), (300, 320, 200, "plain")])
+def test_layer_norm_folded_into_gemm(m, c, n, kind):
+    """gemm(ln=...) on the raw rows == gemm(layer_norm(rows)): compared against the fp32 composition, and required to be
+    at least as close to it as the two-kernel bf16 path (which rounds the normalised rows to bf16 in between)."""
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    # the residual stream: written by a producing GEMM (bias + residual), rows with a non-zero mean
+    a = torch.randn(m, c, generator=g, device="cuda").to(bf16)
+    w0 = (torch.randn(c, c, generator=g, device="cuda") * c ** -0.5).to(bf16)
+    res = (torch.randn(m, c, generator=g, device="cuda") * 2 + 0.7).to(bf16)
+    x, st = ops.gemm(a, w0, None, residual=res, want_stats=True)
+    gamma = 1 + 0.3 * torch.randn(c, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(c, generator=g, device="cuda")
+    w = torch.randn(n, c, generator=g, device="cuda") * c ** -0.5
+    b = 0.1 * torch.randn(n, generator=g, device="cuda")
+    ln32 = torch.nn.functional.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    if kind == "geglu":
+        ref = ln32 @ w.t() + b
+        ref = ref[:, :n // 2] * torch.nn.functional.gelu(ref[:, n // 2:])
+        wp, colsum, shift = ops.pack_geglu_ln(w, b, gamma, beta)
+        y = ops.gemm(x, wp, None, geglu=True, ln=(st, colsum, shift, 1e-5))
+        w2, b2 = ops.pack_geglu(w, b)
+        two = ops.gemm(ops.layer_norm(x, gamma, beta, 1e-5), w2, b2, geglu=True)
+    else:
+        ref = ln32 @ w.t() + b
+        wp, colsum, shift = ops.pack_linear_ln(w, gamma, beta, b)
+        y = ops.gemm(x, wp, None, ln=(st, colsum, shift, 1e-5))
+        two = ops.gemm(ops.layer_norm(x, gamma, beta, 1e-5), ops.pack_linear(w), b)
+    e_fold, e_two = rel_l2(y, ref), rel_l2(two, ref)
+    assert e_fold < 6e-3 and e_fold <= 1.1 * e_two, (e_fold, e_two)
+
+
+@pytest.mark.parametrize("b,t,c,heads", [(2, 1024, 1280, 20), (4, 1024, 1280, 20), (2, 4096, 640, 10)])
+def test_layer_norm_folded_into_bound_cross_attention(b, t, c, heads):
+    """The folded-key product with per-batch-element keys and the per-head softmax epilogue, LayerNorm folded in."""
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(b * t + c)
+    a = torch.randn(b * t, c, generator=g, device="cuda").to(bf16)
+    w0 = (torch.randn(c, c, generator=g, device="cuda") * c ** -0.5).to(bf16)
+    res = (torch.randn(b * t, c, generator=g, device="cuda") * 2 - 0.4).to(bf16)
+    x, st = ops.gemm(a, w0, None, residual=res, want_stats=True)
+    gamma = 1 + 0.3 * torch.randn(c, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(c, generator=g, device="cuda")
+    groups, seg, tk = 2, 80, 77                                        # [uncond; cond] captions shared by b / 2 latents each
+    kp = torch.zeros(groups, heads, seg, c, device="cuda")
+    kp[:, :, :tk] = torch.randn(groups, heads, tk, c, generator=g, device="cuda") * (3.0 * c ** -0.5)
+    kp = kp.reshape(groups, heads * seg, c)
+    kg = (kp * gamma).to(bf16).contiguous()
+    colsum, shift = kg.float().sum(-1).contiguous(), (kp @ beta).contiguous()
+    rpg = t * (b // groups)
+    p = ops.gemm(x.view(b, t, c), kg, softmax_valid=tk, w_rows_per_group=rpg, ln=(st, colsum, shift, 1e-5))
+    ln32 = torch.nn.functional.layer_norm(x.float(), (c,), gamma, beta, 1e-5).view(groups, rpg, c)
+    logits = torch.einsum("gmc,gnc->gmn", ln32, kp).view(groups, rpg, heads, seg)[..., :tk]
+    ref = torch.zeros(groups, rpg, heads, seg, device="cuda")
+    ref[..., :tk] = torch.softmax(logits * 0.6931471805599453, dim=-1)                 # the epilogue works in base 2
+    two = ops.gemm(ops.layer_norm(x, gamma, beta, 1e-5).view(b, t, c), kp.to(bf16).contiguous(), softmax_valid=tk,
+                   w_rows_per_group=rpg)
+    e_fold, e_two = rel_l2(p.view(-1), ref.view(-1)), rel_l2(two.view(-1), ref.view(-1))
+    assert torch.equal(p.view(groups, rpg, heads, seg)[..., tk:], torch.zeros_like(ref[..., tk:]).to(bf16))
+    assert e_fold < 1e-2 and e_fold <= 1.1 * e_two, (e_fold, e_two)

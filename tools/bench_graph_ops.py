@@ -112,6 +112,62 @@ if which == "gnconv":
         t5 = graph_time(lambda i: ops.group_norm_stats(x))
         print(f"conv {N}x{H}x{W} {Cin}->{Cout}: plain conv {t0:6.1f} us | GN(2 kernels)+conv {t1:6.1f} | stats+fused conv {t2:6.1f} | "
               f"fused conv alone {t3:6.1f} (no SiLU {t4:6.1f}) | stats kernel {t5:5.1f}")
+if which == "lnfold":
+    # (1) single GEMMs back to back: plain / writing row statistics / LayerNorm folded in / both
+    for (M, N, K, geglu, residual) in ((2048, 1280, 1280, False, True), (2048, 3840, 1280, False, False),
+                                       (2048, 10240, 1280, True, False), (2048, 1280, 5120, False, True),
+                                       (8192, 640, 640, False, True), (8192, 1920, 640, False, False)):
+        nw = max(2, min(REP, int(160e6 / (N * K * 2)) + 1))
+        ws = [r(N, K, scale=0.03) for _ in range(nw)]
+        bs = torch.randn(N, device=dev); a = r(M, K); res = r(M, N) if residual else None
+        _, st = ops.gemm(r(M, 64), r(K, 64), None, want_stats=True)
+        cs = torch.randn(1, N, device=dev); sh = torch.randn(1, N, device=dev)
+        out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=bf16)
+        t0 = graph_time(lambda i: ops.gemm(a, ws[i % nw], bs, residual=res, geglu=geglu, out=out))
+        t1 = graph_time(lambda i: ops.gemm(a, ws[i % nw], bs, residual=res, geglu=geglu, out=out, ln=(st, cs, sh, 1e-5)))
+        t2 = t3 = float("nan")
+        if not geglu:
+            t2 = graph_time(lambda i: ops.gemm(a, ws[i % nw], bs, residual=res, out=out, want_stats=True))
+            t3 = graph_time(lambda i: ops.gemm(a, ws[i % nw], bs, residual=res, out=out, want_stats=True, ln=(st, cs, sh, 1e-5)))
+        t4 = graph_time(lambda i: ops.layer_norm(a, torch.ones(K, device=dev), torch.zeros(K, device=dev)))
+        print(f"gemm M{M} N{N} K{K} geglu={int(geglu)} res={int(residual)}: plain {t0:6.1f} us | ln in {t1:6.1f} | stats out {t2:6.1f} | "
+              f"both {t3:6.1f} | layer_norm of A alone {t4:5.1f}")
+    # (2) whole transformer blocks in one graph, text context bound
+    from b200sr import modules as md
+    for (B, T, C, H) in ((2, 1024, 1280, 20), (2, 4096, 640, 10)):
+        nblk = 6
+        blocks = [md.BasicTransformerBlock(C, H, 64, context_dim=2048).to(dev) for _ in range(nblk)]
+        ctx = r(2, 77, 2048)
+        for b_ in blocks:
+            b_.attn2.bind_static_context(ctx)
+        x0 = r(B, T, 64); w0 = r(C, 64)
+        def run(fused):
+            if fused:
+                x, st = ops.gemm(x0, w0, None, want_stats=True)
+            else:
+                x, st = ops.gemm(x0, w0, None), None
+            for b_ in blocks:
+                rr = b_(x, context=ctx, stats=st, want_stats=fused)
+                x, st = rr if fused else (rr, None)
+            return x
+        res_ = {}
+        for fused in ((True, False) if md.FUSE_LN_INTO_GEMM else (False,)):
+            with torch.no_grad():
+                y = run(fused); torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    y = run(fused)
+                for _ in range(3): g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10): g.replay()
+                e1.record(); torch.cuda.synchronize()
+                res_[fused] = (e0.elapsed_time(e1) / 10 / nblk * 1e3, y.float().clone())
+        msg = " | ".join(f"{'folded' if k else 'LayerNorm kernels'} {v[0]:7.1f} us/block" for k, v in res_.items())
+        if len(res_) == 2:
+            msg += f" | rel diff {((res_[True][1] - res_[False][1]).norm() / res_[False][1].norm()).item():.2e}"
+        print(f"transformer block B{B} T{T} C{C}: {msg}")
 tot = 0.0
 print(f"{'op':46s} {'us/launch':>9s} {'TF/s|TB/s':>9s} {'n/step':>6s} {'ms/step':>8s}")
 for name, t, rate, n in rows:
