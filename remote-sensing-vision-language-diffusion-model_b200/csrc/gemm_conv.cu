@@ -83,7 +83,7 @@ struct GemmParams {
   int stages;
   int a_stages;  // mode 3: halo-tile ring depth (stages = weight ring depth)
 #ifdef B200SR_GEMM_TRACE
-  long long* trace;  // [grid][16]: 0 mainloop cycles, 1 cycles blocked on the full barrier, 2 chunks, 3 chunks found not ready,
+  long long* trace;  // [grid][32] (16..21: epilogue thread 64: cycles in tmem_ld wait / arithmetic / stores / tile prologue, chunks, tiles): 0 mainloop cycles, 1 cycles blocked on the full barrier, 2 chunks, 3 chunks found not ready,
                      // clock64 stamps: 4 entry, 5 set-up done, 6 producer past griddepcontrol.wait, 7 first stage landed,
                      // 8 last MMA committed, 9 accumulator visible to the epilogue, 10 last store issued, 11 exit;
                      // 12 / 13 globaltimer at entry / exit, 14 SM id
@@ -121,8 +121,15 @@ struct GemmParams {
   const float* ln_shift;    // [weight groups][N]
   float ln_eps;
   float2* ln_stats_out;     // [num_n_blocks][M], nullptr = off
+  // mode 0, fp32 output of a many-tile GEMM (attention scores): the epilogue stages 32 x 32 blocks in shared memory and
+  // stores them with the TMA (tmO) so that whole 128-byte lines leave the SM
+  int epi_tma;
+  // out (and residual) rows are 32-byte aligned and N % 16 == 0: the epilogue moves 32 bytes per thread and instruction
+  // (LDG.256 / STG.256, whole sectors) instead of 16
+  int wide_io;
 };
 
+static constexpr int EPI_SLABS = 4;     // TMA-store epilogue: 32 x 32 fp32 staging blocks per epilogue warp
 static constexpr int SOFTMAX_SEG = 80;  // columns per head segment in the softmax epilogue (77 text tokens, padded)
 
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2): the LayerNorm-fold epilogue's extra arithmetic at half the issue slots.
@@ -218,12 +225,31 @@ __device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
 
 // kXform: the instantiation with the extra GroupNorm warps (320 threads, <= 204 registers); the plain one keeps 192
 // threads and the full register budget its epilogues want.
-// kLn: the instantiation whose epilogue folds a LayerNorm around the GEMM (row statistics in and / or out); kept apart so
-// the plain kernel's register allocation (233, no spills) does not change.
-template <int kCluster, bool kXform, bool kLn = false>
-__global__ void __launch_bounds__(kXform ? GEMM_THREADS_XFORM : GEMM_THREADS, 1)
+// kEpi: the epilogue family.  One instantiation per family keeps the 32-column epilogue loop a few KB of straight code: with
+// every variant in one body (GEGLU's erf, the softmax, fp32 / TMA stores, activations) the loop spanned 24 KB and ran at
+// ~6 cycles per instruction on instruction fetch (tools/gemm_trace.py: 575 cycles for the ~100 instructions of bias + pack).
+enum : int {
+  EPI_GENERAL = 0,   // bias, alpha, rowvec, residual, activation; bf16 or fp32 (direct or TMA-staged) output
+  EPI_XFORM,         // mode 3 with the GroupNorm transform warps; epilogue as EPI_GENERAL without fp32
+  EPI_PLAIN,         // bias, alpha, residual; bf16
+  EPI_GEGLU,         // bias, value * gelu(gate)
+  EPI_SOFTMAX,       // per-head row softmax
+  EPI_LN_PLAIN,      // EPI_PLAIN + LayerNorm fold (row statistics in and / or out)
+  EPI_LN_GEGLU,
+  EPI_LN_SOFTMAX,
+};
+template <int kCluster, int kEpi>
+__global__ void __launch_bounds__(kEpi == EPI_XFORM ? GEMM_THREADS_XFORM : GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+  constexpr bool kXform = kEpi == EPI_XFORM;
+  constexpr bool kLn = kEpi == EPI_LN_PLAIN || kEpi == EPI_LN_GEGLU || kEpi == EPI_LN_SOFTMAX;
+  constexpr bool kSoftmax = kEpi == EPI_SOFTMAX || kEpi == EPI_LN_SOFTMAX;
+  constexpr bool kGeglu = kEpi == EPI_GEGLU || kEpi == EPI_LN_GEGLU;
+  constexpr bool kTail = !kSoftmax && !kGeglu;                       // alpha / residual / plain stores
+  constexpr bool kExtras = kEpi == EPI_GENERAL || kEpi == EPI_XFORM;  // rowvec, activation
+  constexpr bool kF32 = kEpi == EPI_GENERAL;                          // fp32 output
+  constexpr int kResAhead = kXform ? 1 : 2;                           // residual prefetch distance in chunks (XFORM: 168 registers)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Round the dynamic smem base up to 1024 B (swizzle-128B atoms are 1024 B aligned).  The
   // offset is identical in both CTAs of a cluster (same kernel, same static layout), which the
@@ -233,14 +259,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 #ifdef B200SR_GEMM_TRACE
-#define GT(slot) do { if (p.trace != nullptr) p.trace[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#define GT(slot) do { if (p.trace != nullptr) p.trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
   if (threadIdx.x == 0 && p.trace != nullptr) {
     long long gt;
     uint32_t smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.trace[blockIdx.x * 16 + 12] = gt;
-    p.trace[blockIdx.x * 16 + 14] = smid;
+    p.trace[blockIdx.x * 32 + 12] = gt;
+    p.trace[blockIdx.x * 32 + 14] = smid;
     GT(4);
   }
 #else
@@ -269,6 +295,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* s_epi = reinterpret_cast<float*>(smem + ring_bytes + BAR_REGION_BYTES);  // [4 warps][256] staged bias
   float* s_ab = s_epi + 4 * 256;                                                  // fused GN: [Cin] a | [Cin] b of one image
   const bool xform = kXform && halo && p.gn_stats != nullptr;
+  // TMA-store epilogue: [4 warps][EPI_SLABS] slabs of 32 rows x 128 B, 1024-byte aligned (128B swizzle atoms)
+  uint8_t* s_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_ab) + 1023) & ~uintptr_t(1023));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -603,10 +631,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef B200SR_GEMM_TRACE
         t_loop += clock64() - t_begin;
         if (p.trace != nullptr) {
-          p.trace[blockIdx.x * 16 + 0] = t_loop;
-          p.trace[blockIdx.x * 16 + 1] = t_wait;
-          p.trace[blockIdx.x * 16 + 2] = n_chunks;
-          p.trace[blockIdx.x * 16 + 3] = n_late;
+          p.trace[blockIdx.x * 32 + 0] = t_loop;
+          p.trace[blockIdx.x * 32 + 1] = t_wait;
+          p.trace[blockIdx.x * 32 + 2] = n_chunks;
+          p.trace[blockIdx.x * 32 + 3] = n_late;
           GT(8);
         }
 #endif
@@ -719,7 +747,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = sub * 32 + lane;      // accumulator row == TMEM lane
     float* s_bias = s_epi + (warp - 2) * 256;
     const bool ln_in = kLn && p.ln_stats != nullptr;
-    const bool ln_out = kLn && p.ln_stats_out != nullptr;
+    const bool ln_out = kEpi == EPI_LN_PLAIN && p.ln_stats_out != nullptr;
+    const bool epi_tma = kF32 && p.epi_tma != 0;
+    uint32_t slab_i = 0;                      // running slab counter of this warp (TMA-store epilogue)
+#ifdef B200SR_GEMM_TRACE
+    long long e_ld = 0, e_math = 0, e_st = 0, e_pro = 0, e_chunks = 0, e_tiles = 0;
+#define ET(var, since) do { const long long now_ = clock64(); var += now_ - since; since = now_; } while (0)
+#else
+#define ET(var, since) do { } while (0)
+#endif
     float* s_col = s_ab + (warp - 2) * 256;   // LayerNorm fold: column sums of the weight tile (the fused-GN table is mode 3 only)
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -747,11 +783,32 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         group = n;
       }
       // stage bias[n0 .. n0+BN) (zero beyond N) — constant data, independent of earlier kernels
+#ifdef B200SR_GEMM_TRACE
+      long long et = clock64();
+      ++e_tiles;
+#endif
       __syncwarp();
-      const bool has_res = p.residual != nullptr && valid;
+      const bool has_res = kTail && p.residual != nullptr && valid;
       const __nv_bfloat16* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
-      const float* rv_row = (!kLn && p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
-      uint4 res_cur[4], res_nxt[4];
+      const float* rv_row = (kExtras && p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(group) * p.ld_rowvec + n0 : nullptr;
+      // residual chunks in flight: the loads of chunk c + kResAhead are issued at the top of chunk c (one chunk ahead left
+      // ~650 cycles of L2 latency exposed per chunk: tools/gemm_trace.py, 944 vs 284 cycles with / without a residual)
+      uint4 res[kResAhead + 1][4];
+      auto load_res = [&](uint4 (&dst)[4], int cc) {   // cc: column offset of the chunk inside the tile
+        if (p.wide_io) {
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            if (n0 + cc + hq * 16 < p.N)
+              ldg256(res_row + cc + hq * 16, dst[2 * hq], dst[2 * hq + 1]);
+            else
+              dst[2 * hq] = dst[2 * hq + 1] = make_uint4(0, 0, 0, 0);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = (n0 + cc + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + cc) + q) : make_uint4(0, 0, 0, 0);
+        }
+      };
       float ln_rstd = 1.f, ln_nm = 0.f;  // v = rstd * acc - mean * rstd * colsum + shift
       if (!ln_in) {
         for (int j = lane; j < p.BN; j += 32)
@@ -784,8 +841,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (has_res) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
+          for (int d = 0; d < kResAhead; ++d)
+            if (d * 32 < p.BN) load_res(res[d], d * 32);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -805,14 +862,18 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float2 ln_acc1 = make_float2(0.f, 0.f), ln_acc2 = make_float2(0.f, 0.f);  // producer side: (sum, sum of squares), 2 lanes
       if (has_res && !ln_in) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          res_cur[q] = (n0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
+        for (int d = 0; d < kResAhead; ++d)
+          if (d * 32 < p.BN) load_res(res[d], d * 32);
       }
+      ET(e_pro, et);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 64) GT(9);
+#ifdef B200SR_GEMM_TRACE
+      et = clock64();
+#endif
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STAGE_COLS;
-      if (!kXform && p.softmax_valid > 0) {
+      if (kSoftmax) {
         // Row softmax over each SOFTMAX_SEG-column head segment of the accumulator (logits already in log2
         // units), written as bf16 probabilities; columns >= softmax_valid of a segment are padding -> 0.
         for (int sg = 0; sg * SOFTMAX_SEG < p.BN; ++sg) {
@@ -858,34 +919,39 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0);
 #pragma unroll
-            for (int q = 0; q < SOFTMAX_SEG / 8; ++q) {
-              uint4 u;
-              u.x = pack_bf16x2(v[q * 8 + 0] * inv, v[q * 8 + 1] * inv);
-              u.y = pack_bf16x2(v[q * 8 + 2] * inv, v[q * 8 + 3] * inv);
-              u.z = pack_bf16x2(v[q * 8 + 4] * inv, v[q * 8 + 5] * inv);
-              u.w = pack_bf16x2(v[q * 8 + 6] * inv, v[q * 8 + 7] * inv);
-              dst[q] = u;
+            for (int q = 0; q < SOFTMAX_SEG / 8; q += 2) {
+              uint4 u0, u1;
+              u0.x = pack_bf16x2(v[q * 8 + 0] * inv, v[q * 8 + 1] * inv);
+              u0.y = pack_bf16x2(v[q * 8 + 2] * inv, v[q * 8 + 3] * inv);
+              u0.z = pack_bf16x2(v[q * 8 + 4] * inv, v[q * 8 + 5] * inv);
+              u0.w = pack_bf16x2(v[q * 8 + 6] * inv, v[q * 8 + 7] * inv);
+              u1.x = pack_bf16x2(v[q * 8 + 8] * inv, v[q * 8 + 9] * inv);
+              u1.y = pack_bf16x2(v[q * 8 + 10] * inv, v[q * 8 + 11] * inv);
+              u1.z = pack_bf16x2(v[q * 8 + 12] * inv, v[q * 8 + 13] * inv);
+              u1.w = pack_bf16x2(v[q * 8 + 14] * inv, v[q * 8 + 15] * inv);
+              if (p.wide_io) {
+                stg256(dst + q, u0, u1);
+              } else {
+                dst[q] = u0;
+                dst[q + 1] = u1;
+              }
             }
           }
         }
       }
       uint32_t a_cur[32], a_nxt[32];
-      if (kXform || p.softmax_valid <= 0) tmem_ld32(t_row, a_cur);
-      for (int c = 0; c < ((!kXform && p.softmax_valid > 0) ? 0 : p.BN); c += 32) {
+      if (!kSoftmax) tmem_ld32(t_row, a_cur);
+      for (int c = 0; c < (kSoftmax ? 0 : p.BN); c += 32) {
         tmem_ld_wait();
+        ET(e_ld, et);
+#ifdef B200SR_GEMM_TRACE
+        ++e_chunks;
+#endif
         const bool more = c + 32 < p.BN;
-        if (more) {
-          tmem_ld32(t_row + c + 32, a_nxt);
-          if (has_res) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              res_nxt[q] = (n0 + c + 32 + q * 8 < p.N)
-                               ? __ldg(reinterpret_cast<const uint4*>(res_row + c + 32) + q)
-                               : make_uint4(0, 0, 0, 0);
-          }
-        }
+        if (more) tmem_ld32(t_row + c + 32, a_nxt);
+        if (has_res && c + 32 * kResAhead < p.BN) load_res(res[kResAhead], c + 32 * kResAhead);
         const int col0 = n0 + c;
-        if (valid && col0 < p.N) {
+        if ((valid || epi_tma) && col0 < p.N) {   // the TMA clips rows >= M itself; its issue must not depend on the lane
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -905,7 +971,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
             }
           }
-          if (!kXform && p.geglu) {
+          if (kGeglu) {
             // columns [0,16) = value, [16,32) = gate of the same 16 output features
             const long long ocol = col0 >> 1;
             float o[16];
@@ -921,8 +987,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             q1.y = pack_bf16x2(o[10], o[11]);
             q1.z = pack_bf16x2(o[12], o[13]);
             q1.w = pack_bf16x2(o[14], o[15]);
-            reinterpret_cast<uint4*>(dst)[0] = q0;
-            reinterpret_cast<uint4*>(dst)[1] = q1;
+            if (p.wide_io) {
+              stg256(dst, q0, q1);
+            } else {
+              reinterpret_cast<uint4*>(dst)[0] = q0;
+              reinterpret_cast<uint4*>(dst)[1] = q1;
+            }
           } else {
             if (p.alpha != 1.0f) {
 #pragma unroll
@@ -943,8 +1013,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float2 f0 = unpack_bf16x2(res_cur[q].x), f1 = unpack_bf16x2(res_cur[q].y),
-                             f2 = unpack_bf16x2(res_cur[q].z), f3 = unpack_bf16x2(res_cur[q].w);
+                const float2 f0 = unpack_bf16x2(res[0][q].x), f1 = unpack_bf16x2(res[0][q].y),
+                             f2 = unpack_bf16x2(res[0][q].z), f3 = unpack_bf16x2(res[0][q].w);
                 v[q * 8 + 0] += f0.x;
                 v[q * 8 + 1] += f0.y;
                 v[q * 8 + 2] += f1.x;
@@ -955,8 +1025,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[q * 8 + 7] += f3.y;
               }
             }
-            if (kLn) {
-              // no activation in the LayerNorm-folding instantiation (register budget)
+            if (!kExtras) {
+              // activations only in the general families
             } else if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
@@ -967,7 +1037,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = quick_gelu_f(v[j]);
             }
-            if (!kXform && !kLn && p.out_fp32) {
+            ET(e_math, et);
+            if (epi_tma) {
+              // Row r of the warp's 32 x 32 block = 128 bytes; its 16-byte chunk q goes to chunk (q ^ (r & 7)), which is
+              // what the tensor map's 128B swizzle reads back.  EPI_SLABS slabs per warp keep that many stores in flight.
+              uint8_t* slab = s_out + ((warp - 2) * EPI_SLABS + (slab_i % EPI_SLABS)) * 4096;
+              if (lane == 0) tma_store_wait_read<EPI_SLABS - 1>();   // the store that last used this slab has read it
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && p.epi_tma == 1) {
+                tma_store_2d(&tmO, slab, col0, m_blk * BLOCK_M + sub * 32);
+                tma_store_commit();
+              }
+              ++slab_i;
+            } else if (kF32 && p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -976,15 +1064,23 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             } else {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
+              uint4 uu[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uu[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                uu[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                uu[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                uu[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              }
+              if (p.wide_io) {
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq)
+                  if (col0 + hq * 16 < p.N) stg256(dst + hq * 16, uu[2 * hq], uu[2 * hq + 1]);
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 if (col0 + q * 8 < p.N) {
-                  uint4 u;
-                  u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                  u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                  u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                  u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                  reinterpret_cast<uint4*>(dst)[q] = u;
+                  if (!p.wide_io) reinterpret_cast<uint4*>(dst)[q] = uu[q];
                   if (ln_out) {
                     // Statistics of the fp32 values before their rounding to bf16 (the rounding errors average out over
                     // the row: the mean moves by ~2^-9 |x| / sqrt(N)), two columns per packed fp32 instruction.
@@ -996,17 +1092,27 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        ET(e_st, et);
         if (more) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) a_cur[j] = a_nxt[j];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) res_cur[q] = res_nxt[q];
+          for (int d = 0; d < kResAhead; ++d) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res[d][q] = res[d + 1][q];
+          }
         }
       }
       if (ln_out && valid)
         p.ln_stats_out[static_cast<long long>(n_blk) * p.M + row] = make_float2(ln_acc1.x + ln_acc1.y, ln_acc2.x + ln_acc2.y);
       // release this accumulator stage back to the MMA warp
       if (threadIdx.x == 64) GT(10);
+#ifdef B200SR_GEMM_TRACE
+      if (threadIdx.x == 64 && p.trace != nullptr) {
+        long long* tr = p.trace + blockIdx.x * 32 + 16;
+        tr[0] = e_ld; tr[1] = e_math; tr[2] = e_st; tr[3] = e_pro; tr[4] = e_chunks; tr[5] = e_tiles;
+      }
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1022,6 +1128,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  if (kF32 && p.epi_tma != 0 && warp >= 2 && lane == 0) tma_store_wait_all();  // slabs read, results written
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();  // the pair's MMAs / remote arrives must be finished in both CTAs
@@ -1036,7 +1143,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0 && p.trace != nullptr) {
     long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.trace[blockIdx.x * 16 + 13] = gt;
+    p.trace[blockIdx.x * 32 + 13] = gt;
     GT(11);
   }
 #endif
@@ -1080,10 +1187,27 @@ static int pick_bn(int m_blocks, int N, int k_iters, int sms, int cluster) {
 static long long* g_gemm_trace = nullptr;
 #endif
 
+template <int kCluster, int kEpi>
+static cudaError_t launch_epi(int grid, size_t smem_bytes, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                              const CUtensorMap& tmO, const GemmParams& p) {
+  static bool attr_set[64] = {false};  // per device and per instantiation
+  if (first_use_on_device(attr_set)) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(gemm_conv_kernel<kCluster, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  return launch_k(gemm_conv_kernel<kCluster, kEpi>, dim3(grid), dim3(kEpi == EPI_XFORM ? GEMM_THREADS_XFORM : GEMM_THREADS),
+                  smem_bytes, stream, kCluster, tmA, tmB, tmO, p);
+}
+
 template <int kCluster>
-static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams& p,
+                    cudaStream_t stream) {
   // per-channel (a, b) of one image (fused GroupNorm, mode 3) or the weight tile's column sums (LayerNorm fold, mode 0)
-  const int xform_bytes = p.gn_stats != nullptr ? ((p.Cin * 8 + 1023) / 1024) * 1024 : (p.ln_stats != nullptr ? 4096 : 0);
+  const int xform_bytes = p.gn_stats != nullptr ? ((p.Cin * 8 + 1023) / 1024) * 1024
+                          : p.ln_stats != nullptr ? 4096
+                          : p.epi_tma ? 4 * EPI_SLABS * 4096 + 1024   // TMA-store slabs + their alignment
+                                      : 0;
   const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/ - xform_bytes;
   const int b_sub_bytes = (p.BN / kCluster) * BLOCK_K * 2;
   const int stage_bytes = KSUB * (A_STAGE_BYTES + b_sub_bytes);
@@ -1114,28 +1238,25 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& 
 #ifdef B200SR_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
-  static bool attr_set[64] = {false};  // per device (and per kCluster instantiation)
-  if (first_use_on_device(attr_set)) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<kCluster, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(gemm_conv_kernel<kCluster, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_conv_kernel<kCluster, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess)
-      return B200SR_ELAUNCH;
-  }
   const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
   const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
-  const cudaError_t err =
-      p.gn_stats != nullptr
-          ? launch_k(gemm_conv_kernel<kCluster, true>, dim3(grid), dim3(GEMM_THREADS_XFORM), smem_bytes, stream, kCluster, tmA,
-                     tmB, p)
-      : (p.ln_stats != nullptr || p.ln_stats_out != nullptr)
-          ? launch_k(gemm_conv_kernel<kCluster, false, true>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, kCluster,
-                     tmA, tmB, p)
-          : launch_k(gemm_conv_kernel<kCluster, false>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, kCluster, tmA, tmB,
-                     p);
+  const bool ln = p.ln_stats != nullptr || p.ln_stats_out != nullptr;
+  cudaError_t err;
+  if (p.gn_stats != nullptr)
+    err = launch_epi<kCluster, EPI_XFORM>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else if (p.softmax_valid > 0)
+    err = ln ? launch_epi<kCluster, EPI_LN_SOFTMAX>(grid, smem_bytes, stream, tmA, tmB, tmO, p)
+             : launch_epi<kCluster, EPI_SOFTMAX>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else if (p.geglu)
+    err = ln ? launch_epi<kCluster, EPI_LN_GEGLU>(grid, smem_bytes, stream, tmA, tmB, tmO, p)
+             : launch_epi<kCluster, EPI_GEGLU>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else if (ln)
+    err = launch_epi<kCluster, EPI_LN_PLAIN>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else if (p.rowvec != nullptr || p.act != 0 || p.out_fp32)
+    err = launch_epi<kCluster, EPI_GENERAL>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else
+    err = launch_epi<kCluster, EPI_PLAIN>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
   return err == cudaSuccess ? B200SR_OK : B200SR_ELAUNCH;
 }
 
@@ -1215,9 +1336,39 @@ static int finish(const CUtensorMap& tmA, const void* W, GemmParams& p, int real
   uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows)};
   uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
   uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(p.BN / cluster)};
-  const int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
+  int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box);
   if (rc) return rc;
-  return cluster == 2 ? launch_t<2>(tmA, tmB, p, stream) : launch_t<1>(tmA, tmB, p, stream);
+  // fp32 output of a GEMM with at least two tiles per CTA (SR3 / first-stage attention scores, 16384 x 16384): the
+  // per-thread row stores of the plain epilogue (32 scattered 16-byte pieces per instruction) reach 1.9 TB/s and bound
+  // the kernel; TMA stores of staged 32 x 32 blocks write whole lines.  One-tile launches keep the direct stores
+  // (no shared-memory hop on their critical path).
+  static const bool epi_tma_enabled = [] {
+    const char* e = getenv("B200SR_EPI_TMA");
+    return e == nullptr || e[0] != '0';
+  }();
+  {
+    const long long n_out = p.geglu ? p.N / 2 : p.N;
+    const long long esz = p.out_fp32 ? 4 : 2;
+    p.wide_io = !p.out_fp32 && (n_out % 16) == 0 && (p.ldc * esz) % 32 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 &&
+                (p.residual == nullptr || ((p.ldr * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0));
+    static const bool wide_enabled = [] {
+      const char* e = getenv("B200SR_WIDE_IO");
+      return e == nullptr || e[0] != '0';
+    }();
+    if (!wide_enabled) p.wide_io = 0;
+  }
+  CUtensorMap tmO = tmA;
+  p.epi_tma = 0;
+  if (epi_tma_enabled && p.mode == 0 && p.out_fp32 && !p.geglu && p.softmax_valid <= 0 && p.ln_stats == nullptr &&
+      p.ln_stats_out == nullptr && p.residual == nullptr && p.rowvec == nullptr && (p.ldc % 4) == 0 &&
+      static_cast<long long>(p.num_m_blocks / cluster) * p.num_n_blocks >= 2LL * (num_sms() / cluster)) {
+    uint64_t odims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+    uint64_t ostrides[1] = {static_cast<uint64_t>(p.ldc) * 4};
+    uint32_t obox[2] = {32, 32};
+    if (make_tmap_f32(&tmO, p.out, 2, odims, ostrides, obox) == B200SR_OK) p.epi_tma = 1;
+    if (p.epi_tma && getenv("B200SR_EPI_TMA_DRY") != nullptr) p.epi_tma = 2;   // EXPERIMENT: stage but do not store
+  }
+  return cluster == 2 ? launch_t<2>(tmA, tmB, tmO, p, stream) : launch_t<1>(tmA, tmB, tmO, p, stream);
 }
 
 // The N tile gemm_bf16 picks for a plain GEMM (no softmax epilogue, force_bn = 0): a GEMM that writes row statistics

@@ -194,3 +194,24 @@ def test_layer_norm_folded_into_bound_cross_attention(b, t, c, heads):
     e_fold, e_two = rel_l2(p.view(-1), ref.view(-1)), rel_l2(two.view(-1), ref.view(-1))
     assert torch.equal(p.view(groups, rpg, heads, seg)[..., tk:], torch.zeros_like(ref[..., tk:]).to(bf16))
     assert e_fold < 1e-2 and e_fold <= 1.1 * e_two, (e_fold, e_two)
+
+
+@pytest.mark.parametrize("m,n,k", [(16384, 16384, 512), (5000, 4104, 512), (4096, 8192, 64), (9000, 2056, 1280)])
+def test_fp32_output_of_a_many_tile_gemm(m, n, k):
+    """fp32 output with several tiles per CTA (attention scores of the SR3 / first-stage single-head attention) leaves
+    through the TMA-store epilogue: rows / columns beyond M / N are clipped by the tensor map, alpha and bias apply."""
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=g, device="cuda") * 0.5).to(bf16)
+    w = (torch.randn(n, k, generator=g, device="cuda") * 0.5).to(bf16)
+    b = torch.randn(n, generator=g, device="cuda")
+    guard = torch.full((m + 2, n + 8), 7.0, device="cuda")                 # the output is a window of a wider buffer
+    out = guard[1:m + 1, :n]
+    ops.gemm(a, w, b, alpha=0.25, out=out, out_fp32=True)
+    ref = torch.empty(m, n, device="cuda")
+    for r0 in range(0, m, 4096):                                            # fp32 reference in row chunks (memory)
+        ref[r0:r0 + 4096] = (a[r0:r0 + 4096].float() @ w.float().t() + b) * 0.25
+    assert rel_l2(out, ref) < 2e-6
+    assert (out - ref).abs().max().item() < 1e-3
+    assert torch.all(guard[0] == 7.0) and torch.all(guard[m + 1] == 7.0) and torch.all(guard[:, n:] == 7.0)

@@ -112,6 +112,14 @@ if which == "gnconv":
         t5 = graph_time(lambda i: ops.group_norm_stats(x))
         print(f"conv {N}x{H}x{W} {Cin}->{Cout}: plain conv {t0:6.1f} us | GN(2 kernels)+conv {t1:6.1f} | stats+fused conv {t2:6.1f} | "
               f"fused conv alone {t3:6.1f} (no SiLU {t4:6.1f}) | stats kernel {t5:5.1f}")
+if which == "scores":
+    # fp32 attention scores of the single-head attention (SR3 / first stage): M = N = 16384 tokens, K = 512
+    for (M, N, K) in ((16384, 16384, 512), (4096, 4096, 512)):
+        q = r(M, K); k_ = r(N, K)
+        out = torch.empty(M, N, device=dev)
+        t = graph_time(lambda i: ops.gemm(q, k_, None, alpha=0.044, out=out, out_fp32=True))
+        print(f"scores gemm M{M} N{N} K{K} fp32 out: {t:8.1f} us  {2.0 * M * N * K / t / 1e6:7.1f} TF/s  write {M * N * 4 / t / 1e6:6.2f} TB/s"
+              f"  (B200SR_EPI_TMA={os.environ.get('B200SR_EPI_TMA', '1')})")
 if which == "lnfold":
     # (1) single GEMMs back to back: plain / writing row statistics / LayerNorm folded in / both
     for (M, N, K, geglu, residual) in ((2048, 1280, 1280, False, True), (2048, 3840, 1280, False, False),

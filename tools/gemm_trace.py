@@ -15,7 +15,7 @@ bf16 = torch.bfloat16
 def r(*s, scale=0.5): return (torch.randn(*s, device="cuda") * scale).to(bf16)
 def set_trace(t): lib.b200sr_debug_set_gemm_trace(ctypes.c_void_p(0 if t is None else t.data_ptr()))
 
-trace = torch.zeros(512, 16, dtype=torch.int64, device="cuda")
+trace = torch.zeros(512, 32, dtype=torch.int64, device="cuda")
 for (M, N, K, geglu) in ((2048, 1280, 1280, False), (2048, 1280, 5120, False), (2048, 3840, 1280, False), (2048, 10240, 1280, True)):
     a = r(M, K); ws = [r(N, K, scale=0.03) for _ in range(6)]; b = torch.randn(N, device="cuda")
     for i in range(3): ops.gemm(a, ws[i], b, geglu=geglu)
@@ -29,13 +29,33 @@ for (M, N, K, geglu) in ((2048, 1280, 1280, False), (2048, 1280, 5120, False), (
     print(f"M{M} N{N} K{K}: CTAs issuing {len(t)}, chunks/CTA {t[:,2].mean():.0f}, mainloop {t[:,0].mean():.0f} cycles = {t[:,0].mean()/t[:,2].mean():.0f}/chunk, "
           f"blocked on data {t[:,1].mean():.0f} cycles ({100*t[:,1].mean()/t[:,0].mean():.0f}%), chunks found late {100*t[:,3].mean()/t[:,2].mean():.0f}%")
 
+print("\nepilogue of warp 2 lane 0, cycles per 32-column chunk (tmem_ld wait | arithmetic | stores) and per tile before the accumulator wait")
+def epi_case(label, fn):
+    for _ in range(3): fn()
+    trace.zero_(); set_trace(trace); fn(); torch.cuda.synchronize(); set_trace(None)
+    t = trace.cpu(); t = t[t[:, 20] > 0].double()
+    ch, tl = t[:, 20].mean(), t[:, 21].mean()
+    print(f"  {label:58s} tiles/CTA {tl:5.1f} chunks/tile {ch / tl:4.1f} | ld wait {t[:,16].sum()/t[:,20].sum():6.0f} | math {t[:,17].sum()/t[:,20].sum():6.0f} | "
+          f"stores {t[:,18].sum()/t[:,20].sum():6.0f} | prologue/tile {t[:,19].sum()/t[:,21].sum():6.0f}")
+_a = r(2048, 1280); _w = r(1280, 1280, scale=0.03); _b = torch.randn(1280, device="cuda"); _res = r(2048, 1280)
+epi_case("2048x1280x1280 bf16 + bias + residual", lambda: ops.gemm(_a, _w, _b, residual=_res))
+epi_case("2048x1280x1280 bf16 + bias", lambda: ops.gemm(_a, _w, _b))
+_w2 = r(10240, 1280, scale=0.03); _b2 = torch.randn(10240, device="cuda")
+epi_case("2048x10240x1280 geglu", lambda: ops.gemm(_a, _w2, _b2, geglu=True))
+epi_case("2048x10240x1280 bf16 + bias", lambda: ops.gemm(_a, _w2, _b2))
+_q = r(16384, 512); _k = r(16384, 512); _o = torch.empty(16384, 16384, device="cuda")
+epi_case("16384x16384x512 fp32 out (TMA store unless B200SR_EPI_TMA=0)", lambda: ops.gemm(_q, _k, None, alpha=0.044, out=_o, out_fp32=True))
+del _o
+if os.environ.get("TRACE_EPI_ONLY"):
+    raise SystemExit(0)
+
 print("\nfixed-cost timeline, 8 dependent launches per graph (medians over CTAs, ns at the measured SM clock)")
 for (M, N, K, res) in ((2048, 1280, 1280, True), (2048, 1280, 64, False)):
     NL = 8
     a = r(M, K); ws = [r(N, K, scale=0.03) for _ in range(NL)]; b = torch.randn(N, device="cuda")
     resid = r(M, N) if res else None
     outs = [torch.empty(M, N, device="cuda", dtype=bf16) for _ in range(2)]
-    traces = [torch.zeros(512, 16, dtype=torch.int64, device="cuda") for _ in range(NL)]
+    traces = [torch.zeros(512, 32, dtype=torch.int64, device="cuda") for _ in range(NL)]
     def body():
         for i in range(NL):
             set_trace(traces[i])
