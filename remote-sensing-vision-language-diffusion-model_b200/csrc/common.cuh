@@ -123,6 +123,17 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// Explicit shared-space 16-byte accesses: pointers carved out of the dynamic shared memory by integer arithmetic lose their
+// address space and compile to generic LD / ST otherwise.
+__device__ __forceinline__ float4 lds128(const void* ptr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(ptr)));
+  return v;
+}
+__device__ __forceinline__ void sts128(void* ptr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(ptr)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // 256-bit global accesses (sm_100: LDG.256 / STG.256); the address must be 32-byte aligned
 __device__ __forceinline__ void ldg256(const void* ptr, uint4& a, uint4& b) {
   asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

@@ -895,8 +895,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (ln_in) {
 #pragma unroll
             for (int j = 0; j < SOFTMAX_SEG; j += 4) {
-              const float4 c4 = *reinterpret_cast<const float4*>(s_col + sg * SOFTMAX_SEG + j);
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sg * SOFTMAX_SEG + j);
+              const float4 c4 = lds128(s_col + sg * SOFTMAX_SEG + j);
+              const float4 b4 = lds128(s_bias + sg * SOFTMAX_SEG + j);
               ln_apply2(v[j], v[j + 1], ln_rstd, ln_nm, c4.x, c4.y, b4.x, b4.y);
               ln_apply2(v[j + 2], v[j + 3], ln_rstd, ln_nm, c4.z, c4.w, b4.z, b4.w);
             }
@@ -955,9 +955,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + j);
+            const float4 b4 = lds128(s_bias + c + j);
             if (ln_in) {
-              const float4 c4 = *reinterpret_cast<const float4*>(s_col + c + j);
+              const float4 c4 = lds128(s_col + c + j);
               v[j] = __uint_as_float(a_cur[j]);
               v[j + 1] = __uint_as_float(a_cur[j + 1]);
               v[j + 2] = __uint_as_float(a_cur[j + 2]);
@@ -1046,8 +1046,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               __syncwarp();
 #pragma unroll
               for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                sts128(slab + lane * 128 + ((q ^ (lane & 7)) << 4), v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0 && p.epi_tma == 1) {
