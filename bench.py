@@ -476,7 +476,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     achieved = dense_fl / (dense_ms * 1e-3) / 1e12 if dense_ms else 0.0
     peak = pk["bf16_tflops_sustained"]
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
