@@ -82,6 +82,7 @@ struct GemmParams {
   int tiles_w, tiles_h, tiles_n;
   int stages;
   int a_stages;  // mode 3: halo-tile ring depth (stages = weight ring depth)
+  int w_resident;  // mode 3, one N block whose 3 * kc_per_tap weight stages all fit: loaded once per CTA, never recycled
 #ifdef B200SR_GEMM_TRACE
   long long* trace;  // [grid][32] (16..21: epilogue thread 64: cycles in tmem_ld wait / arithmetic / stores / tile prologue, chunks, tiles): 0 mainloop cycles, 1 cycles blocked on the full barrier, 2 chunks, 3 chunks found not ready,
                      // clock64 stamps: 4 entry, 5 set-up done, 6 producer past griddepcontrol.wait, 7 first stage landed,
@@ -380,6 +381,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             pb ^= 1;
           }
         };
+        const bool stream_w = first || !p.w_resident;   // resident weights: the first tile's loads serve every tile
         for (int kh = 0; kh < b_pre; ++kh) load_b(0, kh);
         if (first) pdl_wait();
         for (int cc = 0; cc < p.kc_per_tap; ++cc) {
@@ -400,7 +402,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sa = 0;
             pa ^= 1;
           }
-          for (int kh = (cc == 0 ? b_pre : 0); kh < 3; ++kh) load_b(cc, kh);
+          if (stream_w)
+            for (int kh = (cc == 0 ? b_pre : 0); kh < 3; ++kh) load_b(cc, kh);
         }
       }
     }
@@ -421,9 +424,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_base = smem_u32(smem + sa * A_HALO_BYTES);
           for (int kh = 0; kh < 3; ++kh) {
-            if (!ready) mbar_wait(&full_bar[sb], pb);
+            // resident weights: stage sb = cc * 3 + kh holds this row of this chunk for the whole kernel; only the first
+            // tile waits for it to land
+            const bool wait_w = !p.w_resident || work == work0;
+            if (wait_w && !ready) mbar_wait(&full_bar[sb], pb);
             tc_fence_after();
-            {  // probe the next weight stage now, consume the answer after this row's MMAs are issued
+            if (wait_w) {  // probe the next weight stage now, consume the answer after this row's MMAs are issued
               const int ns = sb + 1 == stages ? 0 : sb + 1;
               ready = mbar_test_wait(&full_bar[ns], ns == 0 ? pb ^ 1 : pb);
             }
@@ -441,10 +447,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   umma2_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | kh | kw | k) != 0);
               }
             }
-            if (kCluster == 1)
-              umma_commit(&empty_bar[sb]);
-            else
-              umma2_commit_mc(&empty_bar[sb], 3);
+            if (!p.w_resident) {
+              if (kCluster == 1)
+                umma_commit(&empty_bar[sb]);
+              else
+                umma2_commit_mc(&empty_bar[sb], 3);
+            }
             if (++sb == stages) {
               sb = 0;
               pb ^= 1;
@@ -750,6 +758,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool ln_out = kEpi == EPI_LN_PLAIN && p.ln_stats_out != nullptr;
     const bool epi_tma = kF32 && p.epi_tma != 0;
     uint32_t slab_i = 0;                      // running slab counter of this warp (TMA-store epilogue)
+    int staged_n_blk = -1;                    // N block whose bias slice this warp's s_bias holds
 #ifdef B200SR_GEMM_TRACE
     long long e_ld = 0, e_math = 0, e_st = 0, e_pro = 0, e_chunks = 0, e_tiles = 0;
 #define ET(var, since) do { const long long now_ = clock64(); var += now_ - since; since = now_; } while (0)
@@ -811,8 +820,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       float ln_rstd = 1.f, ln_nm = 0.f;  // v = rstd * acc - mean * rstd * colsum + shift
       if (!ln_in) {
-        for (int j = lane; j < p.BN; j += 32)
-          s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        // consecutive tiles of a CTA usually share the N block (always, when there is only one): its bias slice is staged
+        // once — the L2 round trip of this load otherwise sits in front of every tile's epilogue
+        if (n_blk != staged_n_blk) {
+          for (int j = lane; j < p.BN; j += 32)
+            s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+          staged_n_blk = n_blk;
+        }
         __syncwarp();
         if (work == work0) pdl_wait();  // residual / rowvec come from earlier kernels
       } else {
@@ -1221,6 +1235,22 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     int stages = (smem_budget - p.a_stages * A_HALO_BYTES) / b_stage_bytes;
     if (stages > MAX_B_STAGES) stages = MAX_B_STAGES;
     if (stages < 2) return B200SR_EINVAL;
+    // Resident weights: a convolution with ONE N block (Cout <= the N tile) whose whole weight set — 3 * kc_per_tap ring
+    // stages — fits next to the halo ring keeps it in shared memory for the life of the CTA.  The SR3 / first-stage
+    // full-resolution convolutions (64 .. 192 -> 64 / 128 channels at 512^2 .. 1024^2, 55 tiles per SM) otherwise re-stream
+    // 36 - 147 KB of weights for every 23 - 46 KB activation tile and wait on a weight barrier per kernel row.
+    static const bool resident_enabled = [] {
+      const char* e = getenv("B200SR_CONV_RESIDENT");
+      return e == nullptr || e[0] != '0';
+    }();
+    p.w_resident = 0;
+    if (resident_enabled && p.num_n_blocks == 1 && 3 * p.kc_per_tap <= stages && 3 * p.kc_per_tap <= MAX_B_STAGES) {
+      p.w_resident = 1;
+      stages = 3 * p.kc_per_tap;
+      // the freed space goes to the halo ring (up to 4 tiles in flight)
+      while (p.a_stages < MAX_A_HALO_STAGES && (smem_budget - (p.a_stages + 1) * A_HALO_BYTES) / b_stage_bytes >= stages)
+        ++p.a_stages;
+    }
     p.stages = stages;
     ring_bytes = static_cast<size_t>(p.a_stages) * A_HALO_BYTES + static_cast<size_t>(stages) * b_stage_bytes;
   } else {

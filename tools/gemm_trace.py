@@ -46,6 +46,10 @@ epi_case("2048x10240x1280 bf16 + bias", lambda: ops.gemm(_a, _w2, _b2))
 _q = r(16384, 512); _k = r(16384, 512); _o = torch.empty(16384, 16384, device="cuda")
 epi_case("16384x16384x512 fp32 out (TMA store unless B200SR_EPI_TMA=0)", lambda: ops.gemm(_q, _k, None, alpha=0.044, out=_o, out_fp32=True))
 del _o
+_x = r(1, 1024, 1024, 64); _wc = r(64, 9 * 64, scale=0.02); _bc = torch.randn(64, device="cuda")
+epi_case("conv3x3 1x1024x1024 64->64 + bias (halo path, resident weights)", lambda: ops.conv3x3(_x, _wc, _bc))
+_x2 = r(1, 512, 512, 128); _wc2 = r(128, 9 * 128, scale=0.02); _bc2 = torch.randn(128, device="cuda")
+epi_case("conv3x3 1x512x512 128->128 + bias", lambda: ops.conv3x3(_x2, _wc2, _bc2))
 if os.environ.get("TRACE_EPI_ONLY"):
     raise SystemExit(0)
 
