@@ -92,6 +92,17 @@ typedef struct b200sr_epilogue {
   const float* ln_shift;
   float ln_eps;
   float* ln_stats_out;         /* [n tiles, M, 2] fp32 or NULL; bf16 output, no geglu / softmax */
+  /* b200sr_gemm_bf16 only: softmax over WHOLE rows of alpha * A W^T in two passes of the same GEMM, for the single-head
+   * attention of width 512 (SR3 SelfAttention, sr3_modules/unet.py:114-143; first-stage AttnBlock, model.py:158-199) whose
+   * output accumulator leaves no tensor memory for a flash-style kernel.  The fp32 score matrix never exists:
+   *   row_softmax = 1  statistics pass: no output matrix (out may be NULL); for every row and N tile the pair
+   *                    (max, sum of 2^(x - max)) of x = alpha * acc over the tile's valid columns -> ln_stats_out
+   *   row_softmax = 2  apply pass: the tile is recomputed and written as bf16 2^(x - M) / L, with (M, L) folded from the
+   *                    ln_parts pairs in ln_stats (= pass 1's ln_stats_out)
+   * alpha carries scale * log2(e); columns >= row_softmax_valid (0 = N) take no part and are written as 0.  No other
+   * epilogue term may be set.                                                                                       */
+  int32_t row_softmax;
+  int32_t row_softmax_valid;
 } b200sr_epilogue;
 
 /* D = A[M,K] * W[N,K]^T with fused epilogue; bf16 operands, fp32 accumulate (tcgen05 / TMEM).
@@ -161,6 +172,10 @@ size_t b200sr_attention_d64_workspace_bytes(int32_t B, int32_t H, int32_t Nq, in
 int b200sr_attention_d64(const void* q, int64_t ldq, int32_t q_col, const void* k, int64_t ldk, int32_t k_col,
                          const void* v, int64_t ldv, int32_t v_col, void* out, int64_t ldo, int32_t B, int32_t H,
                          int32_t Nq, int32_t Nk, float scale, int32_t causal, void* workspace, void* stream);
+
+/* Between the two passes of a row_softmax GEMM: fold the [n_parts, rows, 2] (max, sum) pairs of pass 1 into one
+ * (M, L) pair per row, out [rows, 2]; pass 2 then takes ln_stats = out, ln_parts = 1.                             */
+int b200sr_row_softmax_fold(const float* parts, int32_t n_parts, int64_t rows, float* out, void* stream);
 
 /* y = softmax(x * scale) over the first valid_cols entries of each row (the rest are written as 0: zero-
  * padded keys); x fp32 [rows, cols], y bf16.  SR3 SelfAttention (one head of width C, scores from

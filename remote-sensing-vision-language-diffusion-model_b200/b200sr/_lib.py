@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SR_LIB selects another in-tree build of the same ABI (A/B kernel experiments); default = the product library
 LIB_PATH = os.path.join(_HERE, os.environ.get("B200SR_LIB", "libb200sr.so"))
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_i64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -49,6 +49,8 @@ class Epilogue(C.Structure):
         ("ln_shift", c_void_p),
         ("ln_eps", c_float),
         ("ln_stats_out", c_void_p),
+        ("row_softmax", c_int),
+        ("row_softmax_valid", c_int),
     ]
 
 
@@ -80,6 +82,7 @@ SIGNATURES = {
     "b200sr_num_sms": (c_int, []),
     "b200sr_gemm_bf16": (c_int, [P, c_i64, P, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
     "b200sr_gemm_n_tile": (c_int, [c_int, c_int, c_int]),
+    "b200sr_row_softmax_fold": (c_int, [P, c_int, c_i64, P, P]),
     "b200sr_conv3x3_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(Epilogue), c_int, P]),
     "b200sr_pointwise_small": (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_int, c_float, P]),
     "b200sr_diag_gaussian": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),

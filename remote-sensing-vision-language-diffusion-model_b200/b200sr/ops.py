@@ -485,6 +485,41 @@ def softmax_rows(x: torch.Tensor, scale: float = 1.0, valid_cols: Optional[int] 
 SCORE_CHUNK_BYTES = 1 << 30   # fp32 score rows held at once by single_head_attention (T = 16384: the whole 1 GB matrix)
 
 
+def gemm_row_softmax(a: torch.Tensor, w: torch.Tensor, scale: float, valid_cols: Optional[int] = None,
+                     w_dynamic: bool = True) -> torch.Tensor:
+    """softmax(scale * a @ w.T) over whole rows as bf16 [M, N] (columns >= valid_cols: 0), in two passes of the same GEMM:
+    pass 1 leaves only per-tile (max, sum) statistics, pass 2 recomputes the tile and writes the probabilities — the fp32
+    score matrix never travels through HBM (6 B per score in the three-kernel form, 2 B here)."""
+    _req(w, bf16, "gemm_row_softmax.w")
+    _req(a, bf16, "gemm_row_softmax.a")
+    K, N = a.shape[-1], w.shape[0]
+    a2 = a.reshape(-1, K)
+    if a2.stride(-1) != 1:
+        a2 = a2.contiguous()
+    M, lda = a2.shape[0], a2.stride(0)
+    parts = -(-N // gemm_n_tile(M, N, K))
+    stats = torch.empty(parts, M, 2, dtype=torch.float32, device=a.device)
+    out = torch.empty(M, N, dtype=bf16, device=a.device)
+    lib = _lib.load()
+    folded = torch.empty(M, 2, dtype=torch.float32, device=a.device) if parts > 1 else stats
+    for which in (1, 2):
+        e = _epilogue(out, N, None, None, 0, None, 0, False, False, float(scale) * 1.4426950408889634, 0, 0, 0, 0, w_dynamic)
+        e.row_softmax, e.row_softmax_valid = which, int(valid_cols) if valid_cols is not None else N
+        if which == 1:
+            e.out, e.ln_stats_out = None, stats.data_ptr()
+        else:
+            if parts > 1:
+                check(lib.b200sr_row_softmax_fold(stats.data_ptr(), parts, M, folded.data_ptr(), _stream()), "row_softmax_fold")
+            e.ln_stats, e.ln_parts = folded.data_ptr(), 1
+        with _Timed("gemm", 2.0 * M * N * K, f"M{M} N{N} K{K} row softmax pass {which}"):
+            rc = lib.b200sr_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), M, N, K, C.byref(e), 0, _stream())
+        check(rc, f"gemm_row_softmax pass {which} M={M} N={N} K={K}")
+    return out
+
+
+TWO_PASS_SOFTMAX = True   # single_head_attention: scores recomputed instead of stored (False: score GEMM -> softmax_rows)
+
+
 def single_head_attention(q: torch.Tensor, k: torch.Tensor, v_t: torch.Tensor, scale: float,
                           out_bias: Optional[torch.Tensor] = None, valid_keys: Optional[int] = None) -> torch.Tensor:
     """softmax(q k^T * scale) v for ONE head of width C = 512 (SR3 SelfAttention, sr3_modules/unet.py:114-143; the
@@ -496,13 +531,17 @@ def single_head_attention(q: torch.Tensor, k: torch.Tensor, v_t: torch.Tensor, s
     within SCORE_CHUNK_BYTES (never the T x T matrix: 17 GB at T = 65536)."""
     t, c = q.shape
     tk = k.shape[0]
-    rows = (SCORE_CHUNK_BYTES // (4 * tk)) // 256 * 256
+    two_pass = TWO_PASS_SOFTMAX and tk % 8 == 0
+    rows = (SCORE_CHUNK_BYTES // ((2 if two_pass else 4) * tk)) // 256 * 256
     rows = max(256, min(rows, t))
     out = torch.empty(t, c, dtype=bf16, device=q.device)
     for r0 in range(0, t, rows):
         r1 = min(t, r0 + rows)
-        s = gemm(q[r0:r1], k, out_fp32=True, w_dynamic=True)                    # [rows, Tk] fp32 scores
-        p = softmax_rows(s, scale, valid_cols=valid_keys)
+        if two_pass:
+            p = gemm_row_softmax(q[r0:r1], k, scale, valid_keys)                    # [rows, Tk] bf16 probabilities
+        else:
+            s = gemm(q[r0:r1], k, out_fp32=True, w_dynamic=True)                    # [rows, Tk] fp32 scores
+            p = softmax_rows(s, scale, valid_cols=valid_keys)
         gemm(p, v_t, out_bias, w_dynamic=True, out=out[r0:r1])
     return out
 

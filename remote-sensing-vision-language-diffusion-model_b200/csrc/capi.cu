@@ -109,6 +109,7 @@ int group_norm_stats(const void* x, int N, int HW, int C, int groups, float eps,
 int layer_norm(const void* x, void* y, const float* weight, const float* bias, int M, int C, float eps,
                cudaStream_t stream);
 int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream);
+int row_softmax_fold(const float* parts, int n_parts, long long rows, float* out, cudaStream_t stream);
 int attention_d64(const void* q, long long ldq, int q_col, const void* k, long long ldk, int k_col, const void* v,
                   long long ldv, int v_col, void* out, long long ldo, int B, int H, int Nq, int Nk, float scale,
                   int causal, void* workspace, cudaStream_t stream);
@@ -178,6 +179,8 @@ static EpilogueArgs to_args(const b200sr_epilogue* e) {
   a.ln_shift = e->ln_shift;
   a.ln_eps = e->ln_eps;
   a.ln_stats_out = e->ln_stats_out;
+  a.row_softmax = e->row_softmax;
+  a.row_softmax_valid = e->row_softmax_valid;
   return a;
 }
 
@@ -188,7 +191,7 @@ using namespace b200sr;
 
 extern "C" {
 
-int b200sr_abi_version(void) { return 4; }
+int b200sr_abi_version(void) { return 5; }
 int b200sr_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200SR_ENODEV;
@@ -245,6 +248,9 @@ int b200sr_layer_norm(const void* x, void* y, const float* weight, const float* 
                       void* stream) {
   if (x == nullptr || y == nullptr) return B200SR_EINVAL;
   return layer_norm(x, y, weight, bias, M, C, eps, S(stream));
+}
+int b200sr_row_softmax_fold(const float* parts, int32_t n_parts, int64_t rows, float* out, void* stream) {
+  return row_softmax_fold(parts, n_parts, rows, out, S(stream));
 }
 int b200sr_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t valid_cols, float scale,
                         void* stream) {

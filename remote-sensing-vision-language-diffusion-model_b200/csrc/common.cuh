@@ -412,6 +412,8 @@ struct EpilogueArgs {
   const float* ln_shift;
   float ln_eps;
   float* ln_stats_out;      // GEMM only: per-row partial (sum, sum of squares) of the stored bf16 output, [n tiles][M][2]
+  int row_softmax;          // GEMM only: two-pass softmax over whole rows (1 = statistics pass, 2 = apply pass)
+  int row_softmax_valid;
 };
 
 }  // namespace b200sr

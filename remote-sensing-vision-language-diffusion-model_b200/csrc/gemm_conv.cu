@@ -122,6 +122,10 @@ struct GemmParams {
   const float* ln_shift;    // [weight groups][N]
   float ln_eps;
   float2* ln_stats_out;     // [num_n_blocks][M], nullptr = off
+  // mode 0, two-pass softmax over whole rows (single-head attention at widths the flash kernel cannot hold): 1 = statistics
+  // pass (writes (max, sum of exp2) per row and N tile to ln_stats_out, no output matrix), 2 = apply pass (reads ln_stats)
+  int row_softmax;
+  int row_softmax_valid;    // columns >= this take no part (written as 0)
   // mode 0, fp32 output of a many-tile GEMM (attention scores): the epilogue stages 32 x 32 blocks in shared memory and
   // stores them with the TMA (tmO) so that whole 128-byte lines leave the SM
   int epi_tma;
@@ -152,6 +156,12 @@ __device__ __forceinline__ void stats_acc2(float2& s1, float2& s2, float v0, flo
       "mov.b64 {%0, %1}, a1;\n\tmov.b64 {%2, %3}, a2;\n\t}"
       : "+f"(s1.x), "+f"(s1.y), "+f"(s2.x), "+f"(s2.y)
       : "f"(v0), "f"(v1));
+}
+
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -238,6 +248,8 @@ enum : int {
   EPI_LN_PLAIN,      // EPI_PLAIN + LayerNorm fold (row statistics in and / or out)
   EPI_LN_GEGLU,
   EPI_LN_SOFTMAX,
+  EPI_RS_STATS,      // row softmax over the WHOLE row, pass 1: per row and N tile (max, sum of exp2) of alpha * acc; no output
+  EPI_RS_APPLY,      // pass 2: exp2(alpha * acc - M) / L as bf16, (M, L) folded from the pass-1 partials
 };
 template <int kCluster, int kEpi>
 __global__ void __launch_bounds__(kEpi == EPI_XFORM ? GEMM_THREADS_XFORM : GEMM_THREADS, 1)
@@ -247,7 +259,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool kLn = kEpi == EPI_LN_PLAIN || kEpi == EPI_LN_GEGLU || kEpi == EPI_LN_SOFTMAX;
   constexpr bool kSoftmax = kEpi == EPI_SOFTMAX || kEpi == EPI_LN_SOFTMAX;
   constexpr bool kGeglu = kEpi == EPI_GEGLU || kEpi == EPI_LN_GEGLU;
-  constexpr bool kTail = !kSoftmax && !kGeglu;                       // alpha / residual / plain stores
+  constexpr bool kRsStats = kEpi == EPI_RS_STATS;
+  constexpr bool kRsApply = kEpi == EPI_RS_APPLY;
+  constexpr bool kRs = kRsStats || kRsApply;
+  constexpr bool kTail = !kSoftmax && !kGeglu && !kRs;               // alpha / residual / plain stores
   constexpr bool kExtras = kEpi == EPI_GENERAL || kEpi == EPI_XFORM;  // rowvec, activation
   constexpr bool kF32 = kEpi == EPI_GENERAL;                          // fp32 output
   constexpr int kResAhead = kXform ? 1 : 2;                           // residual prefetch distance in chunks (XFORM: 168 registers)
@@ -819,7 +834,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
       float ln_rstd = 1.f, ln_nm = 0.f;  // v = rstd * acc - mean * rstd * colsum + shift
-      if (!ln_in) {
+      float rs_m = -INFINITY, rs_l = 0.f;   // row softmax: running (max, sum) of pass 1 / (M, 1 / L) of pass 2
+      if (kRs) {
+        if (work == work0) pdl_wait();
+        if (kRsApply && valid) {
+          // fold the pass-1 partials of this row: M = max m_q, L = sum l_q 2^(m_q - M); independent loads, one pass
+          for (int q = 0; q < p.ln_parts; ++q) {
+            const float2 t = __ldg(p.ln_stats + static_cast<long long>(q) * p.M + row);
+            const float m_new = fmaxf(rs_m, t.x);
+            if (m_new > -INFINITY) {
+              rs_l = rs_l * ex2_approx_f(rs_m - m_new) + t.y * ex2_approx_f(t.x - m_new);
+              rs_m = m_new;
+            }
+          }
+          rs_l = rs_l > 0.f ? 1.0f / rs_l : 0.f;
+        }
+      } else if (!ln_in) {
         // consecutive tiles of a CTA usually share the N block (always, when there is only one): its bias slice is staged
         // once — the L2 round trip of this load otherwise sits in front of every tile's epilogue
         if (n_blk != staged_n_blk) {
@@ -965,7 +995,52 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (more) tmem_ld32(t_row + c + 32, a_nxt);
         if (has_res && c + 32 * kResAhead < p.BN) load_res(res[kResAhead], c + 32 * kResAhead);
         const int col0 = n0 + c;
-        if ((valid || epi_tma) && col0 < p.N) {   // the TMA clips rows >= M itself; its issue must not depend on the lane
+        if (kRs) {
+          if (valid && col0 < p.N) {
+            float v[32];
+            const int left = p.row_softmax_valid - col0;   // columns of this chunk that take part
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j < left ? __uint_as_float(a_cur[j]) * p.alpha : -INFINITY;
+            if (kRsStats) {
+              float cmax = v[0];
+#pragma unroll
+              for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+              const float m_new = fmaxf(rs_m, cmax);
+              if (m_new > -INFINITY) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  s0 += ex2_approx_f(v[j] - m_new);
+                  s1 += ex2_approx_f(v[j + 1] - m_new);
+                }
+                rs_l = rs_l * ex2_approx_f(rs_m - m_new) + (s0 + s1);
+                rs_m = m_new;
+              }
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
+              uint4 uu[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float e[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) e[t] = ex2_approx_f(v[q * 8 + t] - rs_m) * rs_l;   // 2^-inf = 0 for masked columns
+                uu[q].x = pack_bf16x2(e[0], e[1]);
+                uu[q].y = pack_bf16x2(e[2], e[3]);
+                uu[q].z = pack_bf16x2(e[4], e[5]);
+                uu[q].w = pack_bf16x2(e[6], e[7]);
+              }
+              if (p.wide_io) {
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq)
+                  if (col0 + hq * 16 < p.N) stg256(dst + hq * 16, uu[2 * hq], uu[2 * hq + 1]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (col0 + q * 8 < p.N) reinterpret_cast<uint4*>(dst)[q] = uu[q];
+              }
+            }
+          }
+        } else if ((valid || epi_tma) && col0 < p.N) {   // the TMA clips rows >= M itself; its issue must not depend on the lane
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -1116,6 +1191,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (kRsStats && valid) p.ln_stats_out[static_cast<long long>(n_blk) * p.M + row] = make_float2(rs_m, rs_l);
       if (ln_out && valid)
         p.ln_stats_out[static_cast<long long>(n_blk) * p.M + row] = make_float2(ln_acc1.x + ln_acc1.y, ln_acc2.x + ln_acc2.y);
       // release this accumulator stage back to the MMA warp
@@ -1218,7 +1294,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
                     cudaStream_t stream) {
   // per-channel (a, b) of one image (fused GroupNorm, mode 3) or the weight tile's column sums (LayerNorm fold, mode 0)
   const int xform_bytes = p.gn_stats != nullptr ? ((p.Cin * 8 + 1023) / 1024) * 1024
-                          : p.ln_stats != nullptr ? 4096
+                          : (p.ln_stats != nullptr && p.row_softmax == 0) ? 4096
                           : p.epi_tma ? 4 * EPI_SLABS * 4096 + 1024   // TMA-store slabs + their alignment
                                       : 0;
   const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - BAR_REGION_BYTES - 4096 /*epilogue bias staging*/ - xform_bytes;
@@ -1270,9 +1346,13 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
   const int work = (p.num_m_blocks / kCluster) * p.num_n_blocks;
   const int slots = num_sms() / kCluster;
   const int grid = (work < slots ? work : slots) * kCluster;
-  const bool ln = p.ln_stats != nullptr || p.ln_stats_out != nullptr;
+  const bool ln = p.row_softmax == 0 && (p.ln_stats != nullptr || p.ln_stats_out != nullptr);
   cudaError_t err;
-  if (p.gn_stats != nullptr)
+  if (p.row_softmax == 1)
+    err = launch_epi<kCluster, EPI_RS_STATS>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else if (p.row_softmax == 2)
+    err = launch_epi<kCluster, EPI_RS_APPLY>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
+  else if (p.gn_stats != nullptr)
     err = launch_epi<kCluster, EPI_XFORM>(grid, smem_bytes, stream, tmA, tmB, tmO, p);
   else if (p.softmax_valid > 0)
     err = ln ? launch_epi<kCluster, EPI_LN_SOFTMAX>(grid, smem_bytes, stream, tmA, tmB, tmO, p)
@@ -1318,6 +1398,24 @@ static int fill_epilogue(GemmParams& p, const EpilogueArgs& e) {
   p.ln_shift = e.ln_shift;
   p.ln_eps = e.ln_eps;
   p.ln_stats_out = reinterpret_cast<float2*>(e.ln_stats_out);
+  p.row_softmax = e.row_softmax;
+  p.row_softmax_valid = e.row_softmax_valid > 0 ? e.row_softmax_valid : p.N;
+  if (e.row_softmax != 0) {
+    // two-pass row softmax: plain GEMM, no other epilogue term; pass 1 writes statistics only, pass 2 bf16 probabilities
+    if (p.mode != 0 || e.row_softmax < 0 || e.row_softmax > 2 || e.geglu || e.out_fp32 || e.residual != nullptr ||
+        e.rowvec != nullptr || e.bias != nullptr || e.act != 0 || e.softmax_valid != 0 || e.a_gn_stats != nullptr ||
+        e.ln_colsum != nullptr || e.ln_shift != nullptr)
+      return B200SR_EINVAL;
+    if (e.row_softmax == 1 && (e.ln_stats_out == nullptr || e.ln_stats != nullptr)) return B200SR_EINVAL;
+    if (e.row_softmax == 2 && (e.ln_stats == nullptr || e.ln_parts <= 0 || e.ln_stats_out != nullptr || e.out == nullptr))
+      return B200SR_EINVAL;
+    if ((p.N % 8) != 0 || (e.row_softmax == 2 && (e.ldc % 8) != 0)) return B200SR_EINVAL;
+    p.out = e.out;
+    p.ldc = e.ldc;
+    p.alpha = e.alpha;
+    p.w_dynamic = e.w_dynamic;
+    return B200SR_OK;
+  }
   if (e.ln_stats != nullptr &&
       (p.mode != 0 || e.ln_parts <= 0 || e.ln_colsum == nullptr || e.ln_shift == nullptr || e.a_gn_stats != nullptr))
     return B200SR_EINVAL;

@@ -781,6 +781,35 @@ softmax_rows_block_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict
   }
 }
 
+// Two-pass row softmax (b200sr_gemm_bf16 with row_softmax = 1 / 2): fold the per-N-tile (max, sum of 2^(x - max)) pairs of
+// pass 1 into one (M, L) pair per row, so that pass 2 reads 8 bytes per row instead of chaining `parts` dependent updates
+// in front of every tile's epilogue (measured: 705 us instead of ~200 for the 16384 x 16384 apply pass).
+__global__ void __launch_bounds__(256) row_softmax_fold_kernel(const float2* __restrict__ parts, int n_parts, long long rows,
+                                                                float2* __restrict__ out) {
+  pdl_wait();
+  const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row < rows) {
+    float m = -INFINITY;
+    for (int q = 0; q < n_parts; ++q) m = fmaxf(m, __ldg(&parts[q * rows + row]).x);   // independent loads
+    float l = 0.f;
+    for (int q = 0; q < n_parts; ++q) {
+      const float2 t = __ldg(&parts[q * rows + row]);
+      l += t.y * exp2f(t.x - m);
+    }
+    out[row] = make_float2(m, l);
+  }
+  pdl_launch_dependents();
+}
+
+int row_softmax_fold(const float* parts, int n_parts, long long rows, float* out, cudaStream_t stream) {
+  if (parts == nullptr || out == nullptr || n_parts <= 0 || rows <= 0) return B200SR_EINVAL;
+  const unsigned grid = static_cast<unsigned>((rows + 255) / 256);
+  return launch_k(row_softmax_fold_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const float2*>(parts), n_parts,
+                  rows, reinterpret_cast<float2*>(out)) == cudaSuccess
+             ? B200SR_OK
+             : B200SR_ELAUNCH;
+}
+
 int softmax_rows(const float* x, void* y, int rows, int cols, int valid, float scale, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0 || valid <= 0 || valid > cols) return B200SR_EINVAL;
   if (cols > 1024 && cols <= 32768 && (cols % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&

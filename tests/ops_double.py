@@ -77,6 +77,11 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_group=0, geglu
     return (y, stats) if want_stats else y
 
 
+def gemm_row_softmax(a, w, scale, valid_cols=None, w_dynamic=True):
+    s = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
+    return softmax_rows(s, scale, valid_cols=valid_cols)
+
+
 class RowStats:
     def __init__(self, buf, parts, dim):
         self.buf, self.parts, self.dim = buf, parts, dim

@@ -215,3 +215,43 @@ def test_fp32_output_of_a_many_tile_gemm(m, n, k):
     assert rel_l2(out, ref) < 2e-6
     assert (out - ref).abs().max().item() < 1e-3
     assert torch.all(guard[0] == 7.0) and torch.all(guard[m + 1] == 7.0) and torch.all(guard[:, n:] == 7.0)
+
+
+@pytest.mark.parametrize("m,n,valid", [(4096, 4096, None), (1000, 16384, 16001), (256, 1024, 77), (16384, 16384, None),
+                                       (300, 2056, 2050)])
+def test_two_pass_row_softmax_gemm(m, n, valid):
+    """softmax(scale * q k^T) over whole rows from two passes of the GEMM (statistics, then probabilities) against torch on
+    the fp32 product; masked columns are exactly 0 and every row sums to 1."""
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    k_dim = 512
+    q = (torch.randn(m, k_dim, generator=g, device="cuda") * 0.7).to(bf16)
+    k = (torch.randn(n, k_dim, generator=g, device="cuda") * 0.7).to(bf16)
+    scale = k_dim ** -0.5
+    p = ops.gemm_row_softmax(q, k, scale, valid)
+    v = n if valid is None else valid
+    assert p.dtype == bf16 and p.shape == (m, n)
+    assert torch.equal(p[:, v:], torch.zeros_like(p[:, v:]))
+    worst = 0.0
+    for r0 in range(0, m, 2048):
+        ref = torch.softmax((q[r0:r0 + 2048].float() @ k.float().t())[:, :v] * scale, dim=-1)
+        worst = max(worst, rel_l2(p[r0:r0 + 2048, :v], ref))
+        assert torch.allclose(p[r0:r0 + 2048].float().sum(-1), torch.ones(ref.shape[0], device="cuda"), atol=2e-2)
+    assert worst < 4e-3, worst
+
+
+def test_single_head_attention_two_pass_equals_three_kernel_form(monkeypatch):
+    from b200sr import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    t, c = 4096, 512
+    q, k, v = ((torch.randn(t, c, generator=g, device="cuda") * 0.5).to(bf16) for _ in range(3))
+    bias = torch.randn(c, generator=g, device="cuda")
+    v_t = v.t().contiguous()
+    monkeypatch.setattr(ops, "TWO_PASS_SOFTMAX", True)
+    a = ops.single_head_attention(q, k, v_t, c ** -0.5, bias)
+    monkeypatch.setattr(ops, "TWO_PASS_SOFTMAX", False)
+    b = ops.single_head_attention(q, k, v_t, c ** -0.5, bias)
+    ref = torch.softmax(q.float() @ k.float().t() * c ** -0.5, dim=-1) @ v.float() + bias
+    assert rel_l2(a, ref) < 6e-3 and rel_l2(b, ref) < 6e-3 and rel_l2(a, b) < 4e-3

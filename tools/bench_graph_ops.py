@@ -120,6 +120,21 @@ if which == "scores":
         t = graph_time(lambda i: ops.gemm(q, k_, None, alpha=0.044, out=out, out_fp32=True))
         print(f"scores gemm M{M} N{N} K{K} fp32 out: {t:8.1f} us  {2.0 * M * N * K / t / 1e6:7.1f} TF/s  write {M * N * 4 / t / 1e6:6.2f} TB/s"
               f"  (B200SR_EPI_TMA={os.environ.get('B200SR_EPI_TMA', '1')})")
+if which == "rowsoftmax":
+    for (M, N, K) in ((16384, 16384, 512), (4096, 4096, 512)):
+        q = r(M, K); k_ = r(N, K); v_t = r(K, N)
+        sc = torch.empty(M, N, device=dev); o = torch.empty(M, K, device=dev, dtype=bf16)
+        def three(i):
+            ops.gemm(q, k_, out=sc, out_fp32=True, w_dynamic=True)
+            p_ = ops.softmax_rows(sc, K ** -0.5)
+            ops.gemm(p_, v_t, None, w_dynamic=True, out=o)
+        def two(i):
+            p_ = ops.gemm_row_softmax(q, k_, K ** -0.5)
+            ops.gemm(p_, v_t, None, w_dynamic=True, out=o)
+        t3 = graph_time(three); t2 = graph_time(two)
+        t1 = graph_time(lambda i: ops.gemm_row_softmax(q, k_, K ** -0.5))
+        print(f"single-head attention T{M} C{K}: score GEMM + softmax + PV {t3:8.1f} us | two-pass softmax GEMM + PV {t2:8.1f} us "
+              f"(the two passes alone {t1:8.1f} us)")
 if which == "lnfold":
     # (1) single GEMMs back to back: plain / writing row statistics / LayerNorm folded in / both
     for (M, N, K, geglu, residual) in ((2048, 1280, 1280, False, True), (2048, 3840, 1280, False, False),
