@@ -1138,7 +1138,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 sts128(slab + lane * 128 + ((q ^ (lane & 7)) << 4), v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0 && p.epi_tma == 1) {
+              if (lane == 0) {
                 tma_store_2d(&tmO, slab, col0, m_blk * BLOCK_M + sub * 32);
                 tma_store_commit();
               }
@@ -1493,7 +1493,6 @@ static int finish(const CUtensorMap& tmA, const void* W, GemmParams& p, int real
     uint64_t ostrides[1] = {static_cast<uint64_t>(p.ldc) * 4};
     uint32_t obox[2] = {32, 32};
     if (make_tmap_f32(&tmO, p.out, 2, odims, ostrides, obox) == B200SR_OK) p.epi_tma = 1;
-    if (p.epi_tma && getenv("B200SR_EPI_TMA_DRY") != nullptr) p.epi_tma = 2;   // EXPERIMENT: stage but do not store
   }
   return cluster == 2 ? launch_t<2>(tmA, tmB, tmO, p, stream) : launch_t<1>(tmA, tmB, tmO, p, stream);
 }
