@@ -983,7 +983,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      uint32_t a_cur[32], a_nxt[32];
+      uint32_t a_cur[32];
       if (!kSoftmax) tmem_ld32(t_row, a_cur);
       for (int c = 0; c < (kSoftmax ? 0 : p.BN); c += 32) {
         tmem_ld_wait();
@@ -992,15 +992,39 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ++e_chunks;
 #endif
         const bool more = c + 32 < p.BN;
-        if (more) tmem_ld32(t_row + c + 32, a_nxt);
         if (has_res && c + 32 * kResAhead < p.BN) load_res(res[kResAhead], c + 32 * kResAhead);
         const int col0 = n0 + c;
+        // The accumulator chunk leaves its registers in the first arithmetic step (for every lane: rows beyond M compute
+        // on zeros), so the next chunk's TMEM load can target the same registers and run under the rest of this chunk:
+        // one 32-register buffer instead of two and no copy at the end of the chunk.
+        float v[32];
+        if (kRs) {
+          const int left = p.row_softmax_valid - col0;   // columns of this chunk that take part
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = j < left ? __uint_as_float(a_cur[j]) * p.alpha : -INFINITY;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = lds128(s_bias + c + j);
+            if (ln_in) {
+              const float4 c4 = lds128(s_col + c + j);
+              v[j] = __uint_as_float(a_cur[j]);
+              v[j + 1] = __uint_as_float(a_cur[j + 1]);
+              v[j + 2] = __uint_as_float(a_cur[j + 2]);
+              v[j + 3] = __uint_as_float(a_cur[j + 3]);
+              ln_apply2(v[j], v[j + 1], ln_rstd, ln_nm, c4.x, c4.y, b4.x, b4.y);
+              ln_apply2(v[j + 2], v[j + 3], ln_rstd, ln_nm, c4.z, c4.w, b4.z, b4.w);
+            } else {
+              v[j] = __uint_as_float(a_cur[j]) + b4.x;
+              v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
+              v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
+              v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
+            }
+          }
+        }
+        if (more) tmem_ld32(t_row + c + 32, a_cur);
         if (kRs) {
           if (valid && col0 < p.N) {
-            float v[32];
-            const int left = p.row_softmax_valid - col0;   // columns of this chunk that take part
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = j < left ? __uint_as_float(a_cur[j]) * p.alpha : -INFINITY;
             if (kRsStats) {
               float cmax = v[0];
 #pragma unroll
@@ -1041,25 +1065,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else if ((valid || epi_tma) && col0 < p.N) {   // the TMA clips rows >= M itself; its issue must not depend on the lane
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = lds128(s_bias + c + j);
-            if (ln_in) {
-              const float4 c4 = lds128(s_col + c + j);
-              v[j] = __uint_as_float(a_cur[j]);
-              v[j + 1] = __uint_as_float(a_cur[j + 1]);
-              v[j + 2] = __uint_as_float(a_cur[j + 2]);
-              v[j + 3] = __uint_as_float(a_cur[j + 3]);
-              ln_apply2(v[j], v[j + 1], ln_rstd, ln_nm, c4.x, c4.y, b4.x, b4.y);
-              ln_apply2(v[j + 2], v[j + 3], ln_rstd, ln_nm, c4.z, c4.w, b4.z, b4.w);
-            } else {
-              v[j] = __uint_as_float(a_cur[j]) + b4.x;
-              v[j + 1] = __uint_as_float(a_cur[j + 1]) + b4.y;
-              v[j + 2] = __uint_as_float(a_cur[j + 2]) + b4.z;
-              v[j + 3] = __uint_as_float(a_cur[j + 3]) + b4.w;
-            }
-          }
           if (kGeglu) {
             // columns [0,16) = value, [16,32) = gate of the same 16 output features
             const long long ocol = col0 >> 1;
@@ -1182,8 +1187,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ET(e_st, et);
         if (more) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) a_cur[j] = a_nxt[j];
 #pragma unroll
           for (int d = 0; d < kResAhead; ++d) {
 #pragma unroll
